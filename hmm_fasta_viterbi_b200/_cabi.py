@@ -1,0 +1,231 @@
+"""ctypes binding of the C ABI in include/msv_cuda.h (libmsv_cuda.so, sm_100a CUDA).
+
+There is deliberately no fallback: if the library is missing the import fails, and if no B200 is present every
+``msv_cuda_*`` call raises ``MsvCudaError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmsv_cuda.so")
+
+MSV_OK = 0
+MSV_ERR_INVALID_ARGUMENT = -1
+MSV_ERR_NO_DEVICE = -2
+MSV_ERR_CUDA = -3
+MSV_ERR_BAD_RESIDUE = -4
+MSV_ERR_MODEL_TOO_LONG = -5
+MSV_ERR_OUT_OF_MEMORY = -6
+
+# every symbol include/msv_cuda.h declares (tests check that the .so exports all of them)
+DECLARED_SYMBOLS = (
+    "msv_cuda_abi_version", "msv_cuda_last_error", "msv_cuda_device_count",
+    "msv_host_emission_table", "msv_host_model_transitions", "msv_host_length_transitions", "msv_host_encode",
+    "msv_host_partition_by_cells",
+    "msv_cuda_model_create", "msv_cuda_model_destroy", "msv_cuda_model_geometry",
+    "msv_cuda_db_create", "msv_cuda_db_destroy", "msv_cuda_db_info",
+    "msv_cuda_db_score_device", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
+    "msv_cuda_launch_count",
+)
+
+
+class MsvCudaError(RuntimeError):
+    def __init__(self, status: int, message: str) -> None:
+        super().__init__(f"[msv_cuda status {status}] {message}")
+        self.status = status
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback for the MSV scan.")
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_u8 = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_u64 = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+_fp = C.POINTER(C.c_float)
+
+lib.msv_cuda_abi_version.restype = C.c_int
+lib.msv_cuda_last_error.restype = C.c_char_p
+lib.msv_cuda_device_count.argtypes = [C.POINTER(C.c_int)]
+lib.msv_host_emission_table.argtypes = [_f32, C.c_size_t, _f32]
+lib.msv_host_model_transitions.argtypes = [C.c_size_t, _fp, _fp, _fp]
+lib.msv_host_length_transitions.argtypes = [C.c_size_t, _fp, _fp]
+lib.msv_host_encode.argtypes = [C.c_char_p, C.c_size_t, _u8, C.POINTER(C.c_size_t)]
+lib.msv_host_partition_by_cells.argtypes = [_u64, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
+lib.msv_cuda_model_create.argtypes = [_f32, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_void_p)]
+lib.msv_cuda_model_destroy.argtypes = [C.c_void_p]
+lib.msv_cuda_model_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_size_t)]
+lib.msv_cuda_db_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+lib.msv_cuda_db_destroy.argtypes = [C.c_void_p]
+lib.msv_cuda_db_info.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+lib.msv_cuda_db_score_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.msv_cuda_db_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+lib.msv_cuda_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+lib.msv_cuda_score_sequence.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, _fp]
+lib.msv_cuda_launch_count.restype = C.c_uint64
+lib.msv_cuda_launch_count.argtypes = [C.c_int]
+for _name in DECLARED_SYMBOLS:
+    if _name not in ("msv_cuda_last_error", "msv_cuda_launch_count", "msv_cuda_abi_version"):
+        getattr(lib, _name).restype = C.c_int
+
+
+def check(status: int) -> None:
+    if status != MSV_OK:
+        raise MsvCudaError(status, lib.msv_cuda_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    status = lib.msv_cuda_device_count(C.byref(n))
+    return n.value if status == MSV_OK else 0
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(lib.msv_cuda_launch_count(1 if reset else 0))
+
+
+# ---- host-side model arithmetic -----------------------------------------------------------------------------------
+def emission_table(match_emissions: np.ndarray) -> np.ndarray:
+    m = np.ascontiguousarray(match_emissions, np.float32)
+    table = np.empty((20, m.shape[0]), np.float32)
+    check(lib.msv_host_emission_table(m, m.shape[0], table))
+    return table
+
+
+def model_transitions(model_length: int) -> tuple[np.float32, np.float32, np.float32]:
+    a, b, c = C.c_float(), C.c_float(), C.c_float()
+    check(lib.msv_host_model_transitions(model_length, C.byref(a), C.byref(b), C.byref(c)))
+    return np.float32(a.value), np.float32(b.value), np.float32(c.value)
+
+
+def length_transitions(residues: int) -> tuple[np.float32, np.float32]:
+    a, b = C.c_float(), C.c_float()
+    check(lib.msv_host_length_transitions(residues, C.byref(a), C.byref(b)))
+    return np.float32(a.value), np.float32(b.value)
+
+
+def encode(letters: str) -> np.ndarray:
+    raw = letters.encode("latin-1")
+    codes = np.empty(max(len(raw), 1), np.uint8)
+    bad = C.c_size_t(0)
+    status = lib.msv_host_encode(raw, len(raw), codes, C.byref(bad))
+    if status == MSV_ERR_BAD_RESIDUE:
+        raise KeyError(lib.msv_cuda_last_error().decode())
+    check(status)
+    return codes[: len(raw)]
+
+
+def partition_by_cells(offsets: np.ndarray, parts: int) -> np.ndarray:
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    bounds = (C.c_size_t * (parts + 1))()
+    check(lib.msv_host_partition_by_cells(offsets, len(offsets) - 1, parts, bounds))
+    return np.array(list(bounds), dtype=np.int64)
+
+
+# ---- device objects -------------------------------------------------------------------------------------------------
+def _ptr(a) -> int:
+    """Address of a numpy array / torch tensor / raw int."""
+    if a is None:
+        return 0
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a.data_ptr())  # torch tensor
+
+
+class Model:
+    """Device-resident model (msv_model*)."""
+
+    def __init__(self, emission_scores: np.ndarray, tr_B_Mk, tr_E_C, tr_E_J, device: int = 0) -> None:
+        table = np.ascontiguousarray(emission_scores, np.float32)
+        assert table.ndim == 2 and table.shape[0] == 20
+        self.model_length = int(table.shape[1])
+        self.device = device
+        h = C.c_void_p()
+        check(lib.msv_cuda_model_create(table, self.model_length, float(tr_B_Mk), float(tr_E_C), float(tr_E_J), device,
+                                        C.byref(h)))
+        self.handle = h
+
+    @property
+    def geometry(self) -> dict:
+        g, k, t, s = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        check(lib.msv_cuda_model_geometry(self.handle, C.byref(g), C.byref(k), C.byref(t), C.byref(s)))
+        return {"lanes_per_sequence": g.value, "columns_per_lane": k.value, "threads_per_cta": t.value,
+                "shared_bytes": s.value}
+
+    def score_batch(self, residues, offsets, out=None) -> np.ndarray:
+        """End-to-end call with host buffers (numpy arrays or pinned torch tensors)."""
+        n = len(offsets) - 1
+        if out is None:
+            out = np.empty(n, np.float32)
+        check(lib.msv_cuda_score_batch(self.handle, _ptr(residues), _ptr(offsets), n, _ptr(out)))
+        return out
+
+    def score_sequence(self, codes: np.ndarray) -> np.float32:
+        codes = np.ascontiguousarray(codes, np.uint8)
+        out = C.c_float()
+        check(lib.msv_cuda_score_sequence(self.handle, codes.ctypes.data if codes.size else 0, codes.size, C.byref(out)))
+        return np.float32(out.value)
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            lib.msv_cuda_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Database:
+    """Device-resident packed database (msv_db*)."""
+
+    def __init__(self, residues, offsets, device: int = 0) -> None:
+        self.n = len(offsets) - 1
+        h = C.c_void_p()
+        if isinstance(residues, np.ndarray):
+            residues = np.ascontiguousarray(residues, np.uint8)
+        if isinstance(offsets, np.ndarray):
+            offsets = np.ascontiguousarray(offsets, np.uint64)
+        check(lib.msv_cuda_db_create(device, _ptr(residues), _ptr(offsets), self.n, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def info(self) -> dict:
+        n, total, longest = C.c_size_t(), C.c_uint64(), C.c_uint64()
+        check(lib.msv_cuda_db_info(self.handle, C.byref(n), C.byref(total), C.byref(longest)))
+        return {"n": n.value, "total_residues": total.value, "longest": longest.value}
+
+    def score(self, model: Model) -> np.ndarray:
+        out = np.empty(self.n, np.float32)
+        check(lib.msv_cuda_db_score(model.handle, self.handle, out.ctypes.data))
+        return out
+
+    def score_device(self, model: Model, scores_device, stream: int = 0) -> None:
+        """Asynchronous scan into a device buffer (torch CUDA tensor or raw pointer) on `stream`."""
+        check(lib.msv_cuda_db_score_device(model.handle, self.handle, _ptr(scores_device), stream))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            lib.msv_cuda_db_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,566 @@
+// msv_cuda.cu -- implementation of the C ABI declared in include/msv_cuda.h.
+//
+// Host side of the boundary: model upload (table re-layout for the kernel), database upload + validation +
+// longest-first bucketing, kernel dispatch by geometry, single-sequence latency path.  The kernels themselves are in
+// msv_kernels.cuh.  Reference behaviour replaced: MSV_HMM::parallel_run_on_sequence and its OpenCL helpers
+// (reference algorithms/MSV_HMM.cpp:118-430).
+#include "msv_cuda.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "msv_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+thread_local uint64_t g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define MSV_CUDA_TRY(expr)                                                                                             \
+    do {                                                                                                               \
+        cudaError_t err__ = (expr);                                                                                    \
+        if (err__ != cudaSuccess) {                                                                                    \
+            const int code__ = (err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver) ? MSV_ERR_NO_DEVICE \
+                               : (err__ == cudaErrorMemoryAllocation)                               ? MSV_ERR_OUT_OF_MEMORY \
+                                                                                                    : MSV_ERR_CUDA;    \
+            (void)cudaGetLastError();                                                                                  \
+            return fail(code__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__);        \
+        }                                                                                                              \
+    } while (0)
+
+// ---- kernel registry: one instantiation per (lanes per sequence, columns per lane) ---------------------------------
+constexpr int threads_for(int K) { return K <= 20 ? 1024 : K <= 40 ? 768 : K <= 56 ? 640 : 512; }
+
+using Scan_kernel = void (*)(const msv::Scan_params);
+struct Geometry {
+    int G, K, threads;
+    Scan_kernel fn;
+};
+
+template <int G, int K> constexpr Geometry geometry_entry() { return Geometry{G, K, threads_for(K), msv::msv_scan_kernel<G, K, threads_for(K)>}; }
+
+#define MSV_FOR_EACH_K(X, G)                                                                                           \
+    X(G, 4) X(G, 8) X(G, 12) X(G, 16) X(G, 20) X(G, 24) X(G, 28) X(G, 32) X(G, 36) X(G, 40) X(G, 44) X(G, 48) X(G, 52)  \
+    X(G, 56) X(G, 60) X(G, 64) X(G, 68) X(G, 72) X(G, 76) X(G, 80) X(G, 84) X(G, 88)
+#define MSV_ENTRY(G, K) geometry_entry<G, K>(),
+const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_ENTRY, 8) MSV_FOR_EACH_K(MSV_ENTRY, 16) MSV_FOR_EACH_K(MSV_ENTRY, 32)};
+
+const Geometry* find_geometry(int G, int K) {
+    for (const auto& g : g_geometries)
+        if (g.G == G && g.K == K) return &g;
+    return nullptr;
+}
+
+int round_up4(size_t v) { return static_cast<int>((v + 3) / 4 * 4); }
+
+// Fewer lanes per sequence amortise the per-row bookkeeping over more cells, as long as the row still fits a lane's
+// registers; MSV_CUDA_GEOMETRY="G,K" overrides the choice (tuning aid).
+const Geometry* choose_geometry(size_t columns) {
+    if (const char* env = std::getenv("MSV_CUDA_GEOMETRY")) {
+        int G = 0, K = 0;
+        if (std::sscanf(env, "%d,%d", &G, &K) == 2 && static_cast<size_t>(G) * K >= columns)
+            if (const Geometry* g = find_geometry(G, K)) return g;
+    }
+    constexpr int preferred_K = 64;
+    for (int G : {8, 16, 32}) {
+        const int K = std::max(4, round_up4((columns + G - 1) / G));
+        if (K <= preferred_K || (G == 32 && K <= msv::kMaxColumnsPerLane)) return find_geometry(G, K);
+    }
+    return nullptr;
+}
+
+struct Device_guard {
+    int previous = -1;
+    cudaError_t status;
+    explicit Device_guard(int device) {
+        status = cudaGetDevice(&previous);
+        if (status == cudaSuccess && previous != device) status = cudaSetDevice(device);
+    }
+    ~Device_guard() {
+        if (previous >= 0) (void)cudaSetDevice(previous);
+    }
+};
+
+} // namespace
+
+// ---- opaque handles ---------------------------------------------------------------------------------------------
+struct msv_db {
+    int device = 0;
+    size_t n = 0;
+    uint64_t total = 0;
+    uint64_t longest = 0;
+    // device buffers (grow-only capacities so a workspace database can be refilled without reallocating)
+    uint8_t* d_residues = nullptr;
+    size_t cap_residues = 0;
+    uint64_t* d_offsets = nullptr;
+    uint32_t* d_order = nullptr;
+    float* d_scores = nullptr;
+    size_t cap_n = 0;
+    float2* d_length_tr = nullptr;
+    size_t cap_tr = 0;
+    uint32_t* d_hist = nullptr; // hist | cursor, 2 * kBuckets
+    unsigned int* d_queue = nullptr;
+    unsigned long long* d_first_bad = nullptr;
+    std::vector<float2> h_length_tr; // host copy, extended lazily
+};
+
+struct msv_model {
+    int device = 0;
+    size_t model_length = 0;
+    const Geometry* geo = nullptr;
+    size_t table_bytes = 0;
+    float4* d_table = nullptr;
+    float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
+    int sm_count = 0;
+    msv_db* workspace = nullptr; // reused by msv_cuda_score_batch / msv_cuda_score_sequence
+};
+
+namespace {
+
+constexpr uint32_t kBuckets = 1u << 16;
+
+int db_release(msv_db* db) {
+    if (!db) return MSV_OK;
+    Device_guard guard(db->device);
+    cudaFree(db->d_residues);
+    cudaFree(db->d_offsets);
+    cudaFree(db->d_order);
+    cudaFree(db->d_scores);
+    cudaFree(db->d_length_tr);
+    cudaFree(db->d_hist);
+    cudaFree(db->d_queue);
+    cudaFree(db->d_first_bad);
+    delete db;
+    return MSV_OK;
+}
+
+// (Re)fill `db` from host buffers: upload, validate, per-length transitions, longest-first order.  Work is queued on
+// `stream`; the function returns after the validation result has been read back (one small synchronisation).
+int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n, cudaStream_t stream) {
+    if (n > 0 && (!offsets || offsets[0] != 0)) return fail(MSV_ERR_INVALID_ARGUMENT, "offsets[0] must be 0");
+    if (n >= (1ull << 32) - 1) return fail(MSV_ERR_INVALID_ARGUMENT, "more than 2^32-2 sequences in one database");
+    uint64_t longest = 0;
+    for (size_t q = 0; q < n; ++q) {
+        if (offsets[q + 1] < offsets[q]) return fail(MSV_ERR_INVALID_ARGUMENT, "offsets not monotonic at %zu", q);
+        longest = std::max<uint64_t>(longest, offsets[q + 1] - offsets[q]);
+    }
+    const uint64_t total = n ? offsets[n] : 0;
+    if (total > 0 && !residues) return fail(MSV_ERR_INVALID_ARGUMENT, "residues is NULL");
+    if (longest >= (1ull << 31)) return fail(MSV_ERR_INVALID_ARGUMENT, "sequence longer than 2^31-1 residues");
+
+    // ---- capacities ----
+    const size_t need_res = static_cast<size_t>(total) + msv::kResiduePadBytes + 16;
+    if (need_res > db->cap_residues) {
+        cudaFree(db->d_residues);
+        db->d_residues = nullptr;
+        db->cap_residues = 0;
+        const size_t cap = need_res + need_res / 8;
+        MSV_CUDA_TRY(cudaMalloc(&db->d_residues, cap));
+        db->cap_residues = cap;
+    }
+    if (n + 1 > db->cap_n) {
+        cudaFree(db->d_offsets);
+        cudaFree(db->d_order);
+        cudaFree(db->d_scores);
+        db->d_offsets = nullptr;
+        db->d_order = nullptr;
+        db->d_scores = nullptr;
+        db->cap_n = 0;
+        const size_t cap = n + 1 + n / 8;
+        MSV_CUDA_TRY(cudaMalloc(&db->d_offsets, cap * sizeof(uint64_t)));
+        MSV_CUDA_TRY(cudaMalloc(&db->d_order, cap * sizeof(uint32_t)));
+        MSV_CUDA_TRY(cudaMalloc(&db->d_scores, cap * sizeof(float)));
+        db->cap_n = cap;
+    }
+    if (!db->d_hist) {
+        MSV_CUDA_TRY(cudaMalloc(&db->d_hist, 2 * kBuckets * sizeof(uint32_t)));
+        MSV_CUDA_TRY(cudaMalloc(&db->d_queue, sizeof(unsigned int)));
+        MSV_CUDA_TRY(cudaMalloc(&db->d_first_bad, sizeof(unsigned long long)));
+    }
+
+    // ---- per-length loop/move scores, host libm (reference MSV_HMM.cpp:59-64) ----
+    if (db->h_length_tr.size() < longest + 1) {
+        const size_t from = db->h_length_tr.size();
+        db->h_length_tr.resize(longest + 1);
+        for (size_t L = from; L <= longest; ++L) {
+            float lo, mv;
+            msv_host_length_transitions(L, &lo, &mv);
+            db->h_length_tr[L] = make_float2(lo, mv);
+        }
+    }
+    const bool tr_grew = db->h_length_tr.size() > db->cap_tr;
+    if (tr_grew) {
+        cudaFree(db->d_length_tr);
+        db->d_length_tr = nullptr;
+        db->cap_tr = 0;
+        MSV_CUDA_TRY(cudaMalloc(&db->d_length_tr, db->h_length_tr.size() * sizeof(float2)));
+        MSV_CUDA_TRY(cudaMemcpyAsync(db->d_length_tr, db->h_length_tr.data(), db->h_length_tr.size() * sizeof(float2),
+                                     cudaMemcpyHostToDevice, stream));
+        db->cap_tr = db->h_length_tr.size();
+    }
+
+    // ---- upload ----
+    if (total) MSV_CUDA_TRY(cudaMemcpyAsync(db->d_residues, residues, total, cudaMemcpyHostToDevice, stream));
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_residues + total, 0, msv::kResiduePadBytes + 16, stream));
+    if (n) {
+        MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    } else {
+        MSV_CUDA_TRY(cudaMemsetAsync(db->d_offsets, 0, sizeof(uint64_t), stream));
+    }
+
+    db->n = n;
+    db->total = total;
+    db->longest = longest;
+    if (n == 0) return MSV_OK;
+
+    // ---- validate codes + bucket longest-first on the device ----
+    const unsigned long long none = ~0ull;
+    MSV_CUDA_TRY(cudaMemcpyAsync(db->d_first_bad, &none, sizeof none, cudaMemcpyHostToDevice, stream));
+    if (total) {
+        const uint64_t words = (total + 15) / 16;
+        const int blocks = static_cast<int>(std::min<uint64_t>((words + 255) / 256, 148 * 16));
+        msv::db_validate_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(db->d_residues), words, total,
+                                                             db->d_first_bad);
+        ++g_launches;
+    }
+    uint32_t shift = 0;
+    while ((longest >> shift) >= kBuckets) ++shift;
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_hist, 0, 2 * kBuckets * sizeof(uint32_t), stream));
+    const uint32_t n32 = static_cast<uint32_t>(n);
+    const uint32_t used_buckets = static_cast<uint32_t>(std::min<uint64_t>((longest >> shift) + 1, kBuckets));
+    const int blocks_n = static_cast<int>((n + 255) / 256);
+    msv::db_histogram_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets, n32, shift, used_buckets, db->d_hist);
+    msv::db_scan_kernel<<<1, 1024, 0, stream>>>(db->d_hist, used_buckets, db->d_hist + kBuckets);
+    msv::db_scatter_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets, n32, shift, used_buckets, db->d_hist + kBuckets,
+                                                         db->d_order);
+    g_launches += 3;
+    MSV_CUDA_TRY(cudaGetLastError());
+
+    unsigned long long first_bad = none;
+    MSV_CUDA_TRY(cudaMemcpyAsync(&first_bad, db->d_first_bad, sizeof first_bad, cudaMemcpyDeviceToHost, stream));
+    MSV_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (first_bad != none) {
+        db->n = 0;
+        return fail(MSV_ERR_BAD_RESIDUE, "residue code %u at position %llu is outside 0..19",
+                    static_cast<unsigned>(residues[first_bad]), first_bad);
+    }
+    return MSV_OK;
+}
+
+int launch_scan(msv_model* model, msv_db* db, float* d_scores, cudaStream_t stream) {
+    if (db->n == 0) return MSV_OK;
+    const Geometry* geo = model->geo;
+    msv::Scan_params p{};
+    p.table = model->d_table;
+    p.residues = db->d_residues;
+    p.offsets = db->d_offsets;
+    p.order = db->d_order;
+    p.length_tr = db->d_length_tr;
+    p.scores = d_scores;
+    p.queue_head = db->d_queue;
+    p.n = static_cast<uint32_t>(db->n);
+    p.table_bytes = static_cast<uint32_t>(model->table_bytes);
+    p.tr_by_sequence = 0;
+    p.tr_B_Mk = model->tr_B_Mk;
+    p.tr_E_C = model->tr_E_C;
+    p.tr_E_J = model->tr_E_J;
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, sizeof(unsigned int), stream));
+    // persistent CTAs: one per SM, but never more groups than sequences
+    const size_t groups_per_cta = static_cast<size_t>(geo->threads / geo->G);
+    const int ctas = static_cast<int>(std::max<size_t>(1, std::min<size_t>(model->sm_count, (db->n + groups_per_cta - 1) / groups_per_cta)));
+    int threads = geo->threads;
+    if (ctas == 1) { // latency path: do not launch warps that would find the queue empty
+        const size_t warps = (db->n * geo->G + 31) / 32;
+        threads = static_cast<int>(std::min<size_t>(geo->threads, std::max<size_t>(1, warps) * 32));
+    }
+    geo->fn<<<ctas, threads, model->table_bytes, stream>>>(p);
+    ++g_launches;
+    MSV_CUDA_TRY(cudaGetLastError());
+    return MSV_OK;
+}
+
+} // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+int msv_cuda_abi_version(void) { return MSV_CUDA_ABI_VERSION; }
+
+const char* msv_cuda_last_error(void) { return g_last_error.c_str(); }
+
+uint64_t msv_cuda_launch_count(int reset) {
+    const uint64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int msv_cuda_device_count(int* count) {
+    if (!count) return fail(MSV_ERR_INVALID_ARGUMENT, "count is NULL");
+    *count = 0;
+    cudaError_t err = cudaGetDeviceCount(count);
+    if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        *count = 0;
+        return fail(MSV_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(err));
+    }
+    return MSV_OK;
+}
+
+// ---- host-side model arithmetic (libm, fp32) --------------------------------------------------------------------------
+// Background residue frequencies used for the log-odds ratio; the values HMMER's p7_AminoFrequencies returns and the
+// reference hard-codes (MSV_HMM.cpp:21-27).
+static const float k_background[MSV_ALPHABET] = {0.0787945f, 0.0151600f, 0.0535222f, 0.0668298f, 0.0397062f,
+                                                 0.0695071f, 0.0229198f, 0.0590092f, 0.0594422f, 0.0963728f,
+                                                 0.0237718f, 0.0414386f, 0.0482904f, 0.0395639f, 0.0540978f,
+                                                 0.0683364f, 0.0540687f, 0.0673417f, 0.0114135f, 0.0304133f};
+
+int msv_host_emission_table(const float* match_emissions, size_t model_length, float* table) {
+    if (!match_emissions || !table) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
+    for (size_t col = 0; col < model_length; ++col) {
+        const float* node = match_emissions + col * MSV_ALPHABET;
+        for (int res = 0; res < MSV_ALPHABET; ++res) table[res * model_length + col] = logf(node[res] / k_background[res]);
+    }
+    return MSV_OK;
+}
+
+int msv_host_model_transitions(size_t model_length, float* tr_B_Mk, float* tr_E_C, float* tr_E_J) {
+    if (!tr_B_Mk || !tr_E_C || !tr_E_J) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
+    const volatile float expected_hits = 2.0f; // "nu"; volatile keeps logf a run-time libm call
+    *tr_B_Mk = logf(2.0f / static_cast<float>(model_length * (model_length + 1)));
+    *tr_E_C = logf((expected_hits - 1.0f) / expected_hits);
+    *tr_E_J = logf(1.0f / expected_hits);
+    return MSV_OK;
+}
+
+int msv_host_length_transitions(size_t residues, float* tr_loop, float* tr_move) {
+    if (!tr_loop || !tr_move) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
+    const float denom = static_cast<float>(residues + 3);
+    *tr_loop = logf(static_cast<float>(residues) / denom);
+    *tr_move = logf(3.0f / denom);
+    return MSV_OK;
+}
+
+int msv_host_encode(const char* letters, size_t n, uint8_t* codes, size_t* bad_at) {
+    static const struct Lut {
+        uint8_t v[256];
+        Lut() {
+            std::memset(v, 0xff, sizeof v);
+            const char* order = "ACDEFGHIKLMNPQRSTVWY";
+            for (int i = 0; i < MSV_ALPHABET; ++i) v[static_cast<unsigned char>(order[i])] = static_cast<uint8_t>(i);
+        }
+    } lut;
+    if ((!letters || !codes) && n) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
+    uint8_t worst = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint8_t c = lut.v[static_cast<unsigned char>(letters[i])];
+        codes[i] = c;
+        worst |= c;
+    }
+    if (worst & 0x80) {
+        size_t at = 0;
+        while (lut.v[static_cast<unsigned char>(letters[at])] != 0xff) ++at;
+        if (bad_at) *bad_at = at;
+        return fail(MSV_ERR_BAD_RESIDUE, "letter '%c' at position %zu is not one of ACDEFGHIKLMNPQRSTVWY", letters[at], at);
+    }
+    return MSV_OK;
+}
+
+int msv_host_partition_by_cells(const uint64_t* offsets, size_t n, int parts, size_t* bounds) {
+    if (parts < 1 || !bounds || (n && !offsets)) return fail(MSV_ERR_INVALID_ARGUMENT, "bad partition request");
+    bounds[0] = 0;
+    const uint64_t base = n ? offsets[0] : 0, total = n ? offsets[n] - base : 0;
+    size_t q = 0;
+    for (int part = 1; part < parts; ++part) {
+        // first sequence whose end passes the ideal cut; whichever side of it is closer to the cut wins
+        const uint64_t want = base + total / parts * part + (total % parts) * part / parts;
+        while (q < n && offsets[q + 1] <= want) ++q;
+        if (q < n && want - offsets[q] > offsets[q + 1] - want) ++q;
+        bounds[part] = q;
+    }
+    bounds[parts] = n;
+    for (int part = 1; part <= parts; ++part) bounds[part] = std::max(bounds[part], bounds[part - 1]);
+    return MSV_OK;
+}
+
+// ---- model ----------------------------------------------------------------------------------------------------------
+int msv_cuda_model_create(const float* emission_scores, size_t model_length, float tr_B_Mk, float tr_E_C, float tr_E_J,
+                          int device, msv_model** out) {
+    if (!out) return fail(MSV_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!emission_scores || model_length < 1) return fail(MSV_ERR_INVALID_ARGUMENT, "empty model");
+    int count = 0;
+    if (int rc = msv_cuda_device_count(&count)) return rc;
+    if (count == 0) return fail(MSV_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= count) return fail(MSV_ERR_INVALID_ARGUMENT, "device %d out of range (have %d)", device, count);
+
+    const size_t columns = model_length - 1; // without the dummy M0
+    const Geometry* geo = choose_geometry(columns);
+    if (!geo)
+        return fail(MSV_ERR_MODEL_TOO_LONG, "model of %zu columns exceeds %d lanes x %d columns", columns, 32,
+                    msv::kMaxColumnsPerLane);
+
+    Device_guard guard(device);
+    MSV_CUDA_TRY(guard.status);
+    cudaDeviceProp prop{};
+    MSV_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MSV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major,
+                    prop.minor);
+
+    // kernel layout: [residue][quad q][lane g][4], column = g*K + 4q + c + 1, -inf beyond the model
+    const int G = geo->G, K = geo->K;
+    const size_t floats = static_cast<size_t>(MSV_ALPHABET) * K * G;
+    std::vector<float> laid(floats, -std::numeric_limits<float>::infinity());
+    for (int res = 0; res < MSV_ALPHABET; ++res)
+        for (int q = 0; q < K / 4; ++q)
+            for (int g = 0; g < G; ++g)
+                for (int c = 0; c < 4; ++c) {
+                    const size_t col = static_cast<size_t>(g) * K + 4 * q + c + 1;
+                    if (col <= columns)
+                        laid[((static_cast<size_t>(res) * (K / 4) + q) * G + g) * 4 + c] = emission_scores[res * model_length + col];
+                }
+
+    auto* model = new (std::nothrow) msv_model();
+    if (!model) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+    model->device = device;
+    model->model_length = model_length;
+    model->geo = geo;
+    model->table_bytes = floats * sizeof(float);
+    model->tr_B_Mk = tr_B_Mk;
+    model->tr_E_C = tr_E_C;
+    model->tr_E_J = tr_E_J;
+    model->sm_count = prop.multiProcessorCount;
+    if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < model->table_bytes + 64) {
+        delete model;
+        return fail(MSV_ERR_MODEL_TOO_LONG, "emission table of %zu bytes exceeds shared memory", floats * sizeof(float));
+    }
+    cudaError_t err = cudaMalloc(&model->d_table, model->table_bytes);
+    if (err == cudaSuccess) err = cudaMemcpy(model->d_table, laid.data(), model->table_bytes, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(reinterpret_cast<const void*>(geo->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(model->table_bytes));
+    if (err != cudaSuccess) {
+        cudaFree(model->d_table);
+        delete model;
+        (void)cudaGetLastError();
+        return fail(MSV_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(err));
+    }
+    *out = model;
+    return MSV_OK;
+}
+
+int msv_cuda_model_destroy(msv_model* model) {
+    if (!model) return MSV_OK;
+    db_release(model->workspace);
+    {
+        Device_guard guard(model->device);
+        cudaFree(model->d_table);
+    }
+    delete model;
+    return MSV_OK;
+}
+
+int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane, int* threads_per_cta,
+                            size_t* shared_bytes) {
+    if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
+    if (lanes_per_sequence) *lanes_per_sequence = model->geo->G;
+    if (columns_per_lane) *columns_per_lane = model->geo->K;
+    if (threads_per_cta) *threads_per_cta = model->geo->threads;
+    if (shared_bytes) *shared_bytes = model->table_bytes;
+    return MSV_OK;
+}
+
+// ---- database -------------------------------------------------------------------------------------------------------
+int msv_cuda_db_create(int device, const uint8_t* residues, const uint64_t* offsets, size_t n, msv_db** out) {
+    if (!out) return fail(MSV_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    if (int rc = msv_cuda_device_count(&count)) return rc;
+    if (device < 0 || device >= count) return fail(MSV_ERR_INVALID_ARGUMENT, "device %d out of range (have %d)", device, count);
+    Device_guard guard(device);
+    MSV_CUDA_TRY(guard.status);
+    auto* db = new (std::nothrow) msv_db();
+    if (!db) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+    db->device = device;
+    const int rc = db_fill(db, residues, offsets, n, nullptr);
+    if (rc != MSV_OK) {
+        db_release(db);
+        return rc;
+    }
+    *out = db;
+    return MSV_OK;
+}
+
+int msv_cuda_db_destroy(msv_db* db) { return db_release(db); }
+
+int msv_cuda_db_info(const msv_db* db, size_t* n, uint64_t* total_residues, uint64_t* longest) {
+    if (!db) return fail(MSV_ERR_INVALID_ARGUMENT, "db is NULL");
+    if (n) *n = db->n;
+    if (total_residues) *total_residues = db->total;
+    if (longest) *longest = db->longest;
+    return MSV_OK;
+}
+
+// ---- scoring --------------------------------------------------------------------------------------------------------
+int msv_cuda_db_score_device(msv_model* model, msv_db* db, float* scores_device, void* cuda_stream) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (model->device != db->device) return fail(MSV_ERR_INVALID_ARGUMENT, "model and database live on different devices");
+    if (db->n && !scores_device) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_device is NULL");
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    return launch_scan(model, db, scores_device, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (model->device != db->device) return fail(MSV_ERR_INVALID_ARGUMENT, "model and database live on different devices");
+    if (db->n && !scores_host) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_host is NULL");
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    if (int rc = launch_scan(model, db, db->d_scores, nullptr)) return rc;
+    if (db->n) MSV_CUDA_TRY(cudaMemcpy(scores_host, db->d_scores, db->n * sizeof(float), cudaMemcpyDeviceToHost));
+    return MSV_OK;
+}
+
+int msv_cuda_score_batch(msv_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host) {
+    if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
+    if (n && (!offsets || !scores_host)) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    if (!model->workspace) {
+        model->workspace = new (std::nothrow) msv_db();
+        if (!model->workspace) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+        model->workspace->device = model->device;
+    }
+    msv_db* db = model->workspace;
+    if (int rc = db_fill(db, residues, offsets, n, nullptr)) return rc;
+    if (int rc = launch_scan(model, db, db->d_scores, nullptr)) return rc;
+    if (n) MSV_CUDA_TRY(cudaMemcpy(scores_host, db->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return MSV_OK;
+}
+
+int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score) {
+    if (!score) return fail(MSV_ERR_INVALID_ARGUMENT, "score is NULL");
+    const uint64_t offsets[2] = {0, length};
+    return msv_cuda_score_batch(model, residues, offsets, 1, score);
+}
+
+} // extern "C"

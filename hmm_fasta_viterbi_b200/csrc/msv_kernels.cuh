@@ -1,0 +1,293 @@
+// msv_kernels.cuh -- hand-written sm_100a kernels of the MSV scan.
+//
+// What the kernel computes (per sequence, fp32, only `+` and `max`): the recurrence of the reference's
+// MSV_HMM::run_on_sequence (reference algorithms/MSV_HMM.cpp:96-112), i.e. the fusion of its six OpenCL kernels
+// (algorithms/MSV_kernels.cl:1-65: init_dp, init_N_B, M_states_handler, copy_M, reduction_step, E_J_C_N_B_handler)
+// and of the host loop that launches them 13 times per residue (MSV_HMM.cpp:382-423) into ONE launch per database.
+//
+// How (B200 design, not a translation):
+//   * a GROUP of G lanes (G = 8, 16 or 32) owns one sequence; a warp therefore scans 32/G sequences at once.
+//     Lane g of the group keeps K consecutive model columns  g*K+1 .. g*K+K  of the DP row in REGISTERS (m[K]).
+//     The row never touches memory.
+//   * the k-1 dependency is satisfied inside a lane by updating m[] from the highest column downwards (every cell
+//     reads the not-yet-overwritten left neighbour), and across lanes by ONE __shfl_up_sync per row.
+//   * E = max_k M is a per-lane FMNMX3 tree followed by a group max (CREDUX.MAX.F32 when G == 32, xor-shuffles
+//     otherwise); the special states N/J/C/B are carried redundantly by every lane of the group.
+//   * the emission table ([residue][column]) is staged ONCE per CTA into shared memory by bulk-async (TMA) copies
+//     completing on an mbarrier; its layout [residue][quad][lane][4] makes every access a conflict-free LDS.128.
+//     Columns beyond the model are padded with -inf, so they never win a max.
+//   * CTAs are persistent (one per SM); groups pull sequences longest-first from a global atomic queue, so a warp
+//     is never idle while work remains and long sequences start first.
+//   * residues stream from HBM as aligned 32-bit words (4 residues), prefetched one word ahead.
+// Exactness: every cell performs the same fp32 add on the same operands as the reference; max is exact and
+// order-independent for the non-NaN values that can occur (-inf and finite numbers only), so scores are
+// bit-identical to the reference for any summation order of the E reduction.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace msv {
+
+constexpr int kAlphabet = 20;
+constexpr int kMaxColumnsPerLane = 88;
+constexpr uint32_t kResiduePadBytes = 64; // bytes readable past the last residue of the database
+
+struct Scan_params {
+    const float4* table;      // emission table in kernel layout (global memory), table_bytes long
+    const uint8_t* residues;  // concatenated residue codes, padded by kResiduePadBytes
+    const uint64_t* offsets;  // n + 1
+    const uint32_t* order;    // n sequence indices, longest first
+    const float2* length_tr;  // (tr_loop, tr_move): indexed by length, or by sequence when tr_by_sequence != 0
+    float* scores;            // n, original order
+    unsigned int* queue_head; // work queue cursor, zero before launch
+    uint32_t n;
+    uint32_t table_bytes;
+    uint32_t tr_by_sequence;
+    float tr_B_Mk, tr_E_C, tr_E_J;
+};
+
+// ---- mbarrier / bulk-async (TMA) helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbarrier_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbarrier_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
+// global -> shared bulk copy executed by the TMA unit (SASS: UBLKCP); completion is counted in bytes on `bar`.
+__device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- group max --------------------------------------------------------------------------------------------------
+template <int G> __device__ __forceinline__ float group_max(float v) {
+    if constexpr (G == 32) {
+        float r;
+        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+        return r;
+    } else {
+#pragma unroll
+        for (int d = G / 2; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+        return v;
+    }
+}
+
+// ---- the scan ---------------------------------------------------------------------------------------------------
+template <int G, int K, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params p) {
+    static_assert(G == 8 || G == 16 || G == 32, "lanes per sequence");
+    static_assert(K % 4 == 0 && K >= 4 && K <= kMaxColumnsPerLane, "columns per lane");
+    constexpr int ROW4 = (K / 4) * G; // float4 elements per residue row of the table
+    constexpr uint32_t COPY_CHUNK = 32768;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t table_ready;
+
+    // ---- stage the emission table: one thread programs the TMA unit, everybody waits on the mbarrier ----
+    if (threadIdx.x == 0) mbarrier_init(&table_ready, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbarrier_expect_tx(&table_ready, p.table_bytes);
+        for (uint32_t at = 0; at < p.table_bytes; at += COPY_CHUNK) {
+            const uint32_t bytes = min(COPY_CHUNK, p.table_bytes - at);
+            tma_bulk_load(smem_raw + at, reinterpret_cast<const unsigned char*>(p.table) + at, bytes, &table_ready);
+        }
+    }
+    mbarrier_wait(&table_ready, 0);
+
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
+    const float4* tab_lane = reinterpret_cast<const float4*>(smem_raw) + gl;
+    const float NEG_INF = __int_as_float(0xff800000);
+    const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
+
+    float m[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) m[j] = NEG_INF;
+    float J = NEG_INF, C = NEG_INF, N = 0.0f, B = NEG_INF, loop = 0.0f, move = 0.0f;
+
+    uint32_t remaining = 0, idx = 0;
+    bool active = false, done = false;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues);
+    uint32_t buf = 0, nextw = 0, have = 0x7fffffffu;
+
+    for (;;) {
+        // ---- retire finished sequences, pull new ones (group-uniform control flow) ----
+        while (remaining == 0 && !done) {
+            if (active) {
+                if (gl == 0) p.scores[idx] = C + move; // MSV_HMM.cpp:112
+                active = false;
+            }
+            uint32_t ticket = 0;
+            if (gl == 0) ticket = atomicAdd(p.queue_head, 1u);
+            ticket = __shfl_sync(gmask, ticket, 0, G);
+            if (ticket >= p.n) {
+                done = true;
+                buf = 0;
+                nextw = 0;
+                have = 0x7fffffffu;
+                break;
+            }
+            idx = __ldg(p.order + ticket);
+            const uint64_t begin = __ldg(p.offsets + idx);
+            const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
+            const float2 tr = __ldg(p.length_tr + (p.tr_by_sequence ? idx : len));
+            loop = tr.x;
+            move = tr.y;
+#pragma unroll
+            for (int j = 0; j < K; ++j) m[j] = NEG_INF; // MSV_HMM.cpp:86
+            J = NEG_INF;
+            C = NEG_INF;
+            N = 0.0f;  // MSV_HMM.cpp:96
+            B = move;  // MSV_HMM.cpp:97
+            const uint32_t mis = static_cast<uint32_t>(begin) & 3u;
+            wp = reinterpret_cast<const uint32_t*>(p.residues + (begin - mis));
+            buf = __ldg(wp) >> (8u * mis);
+            nextw = __ldg(wp + 1);
+            wp += 2;
+            have = 4u - mis;
+            remaining = len;
+            active = true;
+        }
+
+        // ---- rows that every group of this warp can run without anyone finishing: warp-uniform trip count ----
+        const uint32_t mine = done ? 0xffffffffu : remaining;
+        const uint32_t steps = (G == 32) ? mine : __reduce_min_sync(0xffffffffu, mine);
+        if (steps == 0xffffffffu) break;
+        if (!done) remaining -= steps;
+
+#pragma unroll 1
+        for (uint32_t t = 0; t < steps; ++t) {
+            const uint32_t x = buf & 0xffu;
+            buf >>= 8;
+            if (--have == 0) {
+                buf = nextw;
+                have = 4;
+                if (!done) nextw = __ldg(wp);
+                ++wp;
+            }
+            const float4* e = tab_lane + x * ROW4;
+            const float bt = B + tBMk; // MSV_HMM.cpp:103, the B -> M_k entry
+            float left = __shfl_up_sync(0xffffffffu, m[K - 1], 1, G);
+            if (gl == 0) left = NEG_INF; // column 0 (dummy M0) stays -inf
+
+            float e0 = NEG_INF, e1 = NEG_INF;
+#pragma unroll
+            for (int q = K / 4 - 1; q >= 0; --q) {
+                const float4 ev = e[q * G];
+                const int j = 4 * q;
+                m[j + 3] = ev.w + fmaxf(m[j + 2], bt);
+                m[j + 2] = ev.z + fmaxf(m[j + 1], bt);
+                m[j + 1] = ev.y + fmaxf(m[j], bt);
+                m[j] = ev.x + fmaxf(q ? m[j - 1] : left, bt);
+                e0 = fmaxf(fmaxf(e0, m[j + 3]), m[j + 2]); // MSV_HMM.cpp:104
+                e1 = fmaxf(fmaxf(e1, m[j + 1]), m[j]);
+            }
+            const float E = group_max<G>(fmaxf(e0, e1));
+
+            J = fmaxf(J + loop, E + tEJ);   // MSV_HMM.cpp:107
+            C = fmaxf(C + loop, E + tEC);   // MSV_HMM.cpp:108
+            N = N + loop;                   // MSV_HMM.cpp:109
+            B = fmaxf(N + move, J + move);  // MSV_HMM.cpp:110
+        }
+    }
+}
+
+// ---- database preparation kernels -------------------------------------------------------------------------------
+// Validate residue codes (reference: unordered_map::at throws on a foreign letter, MSV_HMM.cpp:101) -- 16 B per thread.
+__global__ void db_validate_kernel(const uint4* __restrict__ words, uint64_t n_words16, uint64_t n_bytes,
+                                   unsigned long long* __restrict__ first_bad) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_words16; i += stride) {
+        const uint4 w = words[i];
+        const uint32_t v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // a byte is bad iff it is >= 20: (b + 108) sets bit 7 for b >= 20 (b < 128), or b itself has bit 7
+            const uint32_t t = ((v[k] & 0x7f7f7f7fu) + 0x6c6c6c6cu) | v[k];
+            if (t & 0x80808080u) {
+                for (int b = 0; b < 4; ++b) {
+                    const uint64_t pos = i * 16 + k * 4 + b;
+                    if (pos < n_bytes && ((v[k] >> (8 * b)) & 0xffu) >= kAlphabet) atomicMin(first_bad, static_cast<unsigned long long>(pos));
+                }
+            }
+        }
+    }
+}
+
+// Longest-first bucketing (counting sort on length >> shift), three tiny kernels.
+__global__ void db_histogram_kernel(const uint64_t* __restrict__ offsets, uint32_t n, uint32_t shift, uint32_t buckets,
+                                    uint32_t* __restrict__ hist) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint64_t len = offsets[q + 1] - offsets[q];
+    const uint32_t b = static_cast<uint32_t>(min(len >> shift, static_cast<uint64_t>(buckets - 1)));
+    atomicAdd(hist + b, 1u);
+}
+
+// cursor[b] = number of sequences in buckets longer than b  (exclusive scan from the top bucket down); one CTA.
+__global__ void db_scan_kernel(const uint32_t* __restrict__ hist, uint32_t buckets, uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t partial[1024];
+    const uint32_t per = (buckets + blockDim.x - 1) / blockDim.x;
+    // thread t owns the descending range of buckets [hi - per*t, ...)
+    const int64_t top = static_cast<int64_t>(buckets) - 1 - static_cast<int64_t>(per) * threadIdx.x;
+    uint32_t sum = 0;
+    for (uint32_t k = 0; k < per; ++k) {
+        const int64_t b = top - k;
+        if (b >= 0) sum += hist[b];
+    }
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t t = 0; t < blockDim.x; ++t) {
+            const uint32_t v = partial[t];
+            partial[t] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    uint32_t run = partial[threadIdx.x];
+    for (uint32_t k = 0; k < per; ++k) {
+        const int64_t b = top - k;
+        if (b >= 0) {
+            cursor[b] = run;
+            run += hist[b];
+        }
+    }
+}
+
+__global__ void db_scatter_kernel(const uint64_t* __restrict__ offsets, uint32_t n, uint32_t shift, uint32_t buckets,
+                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint64_t len = offsets[q + 1] - offsets[q];
+    const uint32_t b = static_cast<uint32_t>(min(len >> shift, static_cast<uint64_t>(buckets - 1)));
+    order[atomicAdd(cursor + b, 1u)] = q;
+}
+
+} // namespace msv

@@ -1,0 +1,216 @@
+"""Python mirror of the reference's host interface, driving the C++ host layer (libmsv_host.so) through ctypes.
+
+Class and method names follow the reference (data_readers/Profile_HMM.hpp:21-49,
+data_readers/FASTA_protein_sequences.hpp:9-14, algorithms/MSV_HMM.hpp:17-24) so that parity tests read like the
+reference's own tests.  All parsing and all arithmetic happen in the C++/CUDA libraries; this file only marshals.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _cabi  # noqa: F401  (loads libmsv_cuda.so first so that libmsv_host.so resolves against it)
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmsv_host.so")
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build()")
+lib = C.CDLL(LIB_PATH)
+
+_vp = C.c_void_p
+_f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+lib.msvh_last_error.restype = C.c_char_p
+lib.msvh_profile_load.restype = _vp
+lib.msvh_profile_load.argtypes = [C.c_char_p]
+lib.msvh_profile_free.argtypes = [_vp]
+lib.msvh_profile_model_length.restype = C.c_size_t
+lib.msvh_profile_model_length.argtypes = [_vp]
+lib.msvh_profile_name.restype = C.c_char_p
+lib.msvh_profile_name.argtypes = [_vp]
+lib.msvh_profile_rows.restype = C.c_size_t
+lib.msvh_profile_rows.argtypes = [_vp, C.c_int]
+lib.msvh_profile_copy.argtypes = [_vp, C.c_int, _f32]
+lib.msvh_profile_stats.argtypes = [_vp, _f32]
+lib.msvh_fasta_load.restype = _vp
+lib.msvh_fasta_load.argtypes = [C.c_char_p]
+lib.msvh_fasta_free.argtypes = [_vp]
+lib.msvh_fasta_count.restype = C.c_size_t
+lib.msvh_fasta_count.argtypes = [_vp]
+lib.msvh_fasta_record.restype = C.c_char_p
+lib.msvh_fasta_record.argtypes = [_vp, C.c_size_t]
+lib.msvh_packed_from_fasta_file.restype = _vp
+lib.msvh_packed_from_fasta_file.argtypes = [C.c_char_p, C.POINTER(C.c_size_t)]
+lib.msvh_packed_from_fasta.restype = _vp
+lib.msvh_packed_from_fasta.argtypes = [_vp]
+lib.msvh_packed_synthetic_swissprot_like.restype = _vp
+lib.msvh_packed_synthetic_swissprot_like.argtypes = [C.c_size_t, C.c_uint64]
+lib.msvh_packed_synthetic_long_uniform.restype = _vp
+lib.msvh_packed_synthetic_long_uniform.argtypes = [C.c_size_t, C.c_uint64, C.c_size_t, C.c_size_t]
+lib.msvh_packed_from_arrays.restype = _vp
+lib.msvh_packed_from_arrays.argtypes = [_vp, _vp, C.c_size_t]
+lib.msvh_packed_free.argtypes = [_vp]
+lib.msvh_packed_count.restype = C.c_size_t
+lib.msvh_packed_count.argtypes = [_vp]
+lib.msvh_packed_total.restype = C.c_uint64
+lib.msvh_packed_total.argtypes = [_vp]
+lib.msvh_packed_residues.restype = C.POINTER(C.c_uint8)
+lib.msvh_packed_residues.argtypes = [_vp]
+lib.msvh_packed_offsets.restype = C.POINTER(C.c_uint64)
+lib.msvh_packed_offsets.argtypes = [_vp]
+lib.msvh_msv_create.restype = _vp
+lib.msvh_msv_create.argtypes = [_vp, C.c_int]
+lib.msvh_msv_clone.restype = _vp
+lib.msvh_msv_clone.argtypes = [_vp]
+lib.msvh_msv_free.argtypes = [_vp]
+lib.msvh_msv_length.restype = C.c_size_t
+lib.msvh_msv_length.argtypes = [_vp]
+lib.msvh_msv_run_on_sequence.argtypes = [_vp, C.c_char_p, C.POINTER(C.c_float)]
+lib.msvh_msv_parallel_run_on_sequence.argtypes = [_vp, C.c_char_p, C.c_int, C.POINTER(C.c_float)]
+lib.msvh_msv_parallel_run_on_packed.argtypes = [_vp, _vp, _f32]
+
+
+def _raise(status: int) -> None:
+    message = lib.msvh_last_error().decode(errors="replace")
+    if status == -2:
+        raise KeyError(message)  # std::out_of_range in C++ (foreign residue letter)
+    raise RuntimeError(message)
+
+
+class Profile_HMM:
+    """data_readers/Profile_HMM.hpp:21-49."""
+
+    def __init__(self, file_path: str) -> None:
+        self._h = lib.msvh_profile_load(os.fspath(file_path).encode())
+        if not self._h:
+            _raise(-1)
+        self.model_length = int(lib.msvh_profile_model_length(self._h))
+        self.name = lib.msvh_profile_name(self._h).decode()
+        mats = []
+        for which, cols in ((0, 20), (1, 20), (2, 7)):
+            rows = lib.msvh_profile_rows(self._h, which)
+            buf = np.empty((rows, cols), np.float32)
+            lib.msvh_profile_copy(self._h, which, buf)
+            mats.append(buf)
+        self.match_emissions, self.insert_emissions, self.transitions = mats
+        st = np.empty(6, np.float32)
+        lib.msvh_profile_stats(self._h, st)
+        (self.stats_local_msv_mu, self.stats_local_msv_lambda, self.stats_local_viterbi_mu, self.stats_local_viterbi_lambda,
+         self.stats_local_forward_theta, self.stats_local_forward_lambda) = (np.float32(v) for v in st)
+
+    def __del__(self) -> None:
+        if getattr(self, "_h", None):
+            lib.msvh_profile_free(self._h)
+            self._h = None
+
+
+class FASTA_protein_sequences:
+    """data_readers/FASTA_protein_sequences.hpp:9-14: `.sequences` is a list of '#'-prefixed strings."""
+
+    def __init__(self, file_path: str) -> None:
+        self._h = lib.msvh_fasta_load(os.fspath(file_path).encode())
+        if not self._h:
+            _raise(-1)
+        self.sequences = [lib.msvh_fasta_record(self._h, i).decode("latin-1") for i in range(lib.msvh_fasta_count(self._h))]
+
+    def __del__(self) -> None:
+        if getattr(self, "_h", None):
+            lib.msvh_fasta_free(self._h)
+            self._h = None
+
+
+class Packed_sequences:
+    """Packed device-facing layout (host/data_readers/Packed_sequences.hpp): uint8 codes + uint64 offsets."""
+
+    def __init__(self, handle) -> None:
+        if not handle:
+            _raise(-1)
+        self._h = handle
+
+    @classmethod
+    def from_fasta_file(cls, path: str) -> "Packed_sequences":
+        rejected = C.c_size_t(0)
+        self = cls(lib.msvh_packed_from_fasta_file(os.fspath(path).encode(), C.byref(rejected)))
+        self.rejected = rejected.value
+        return self
+
+    @classmethod
+    def from_fasta(cls, fasta: FASTA_protein_sequences) -> "Packed_sequences":
+        return cls(lib.msvh_packed_from_fasta(fasta._h))
+
+    @classmethod
+    def from_arrays(cls, residues: np.ndarray, offsets: np.ndarray) -> "Packed_sequences":
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        return cls(lib.msvh_packed_from_arrays(residues.ctypes.data, offsets.ctypes.data, len(offsets) - 1))
+
+    @classmethod
+    def synthetic_swissprot_like(cls, count: int, seed: int) -> "Packed_sequences":
+        return cls(lib.msvh_packed_synthetic_swissprot_like(count, seed))
+
+    @classmethod
+    def synthetic_long_uniform(cls, count: int, seed: int, shortest: int, longest: int) -> "Packed_sequences":
+        return cls(lib.msvh_packed_synthetic_long_uniform(count, seed, shortest, longest))
+
+    def __len__(self) -> int:
+        return int(lib.msvh_packed_count(self._h))
+
+    @property
+    def total_residues(self) -> int:
+        return int(lib.msvh_packed_total(self._h))
+
+    @property
+    def residues(self) -> np.ndarray:
+        """Zero-copy view (valid while this object lives)."""
+        n = self.total_residues
+        if n == 0:
+            return np.zeros(0, np.uint8)
+        return np.ctypeslib.as_array(lib.msvh_packed_residues(self._h), shape=(n,))
+
+    @property
+    def offsets(self) -> np.ndarray:
+        return np.ctypeslib.as_array(lib.msvh_packed_offsets(self._h), shape=(len(self) + 1,))
+
+    def __del__(self) -> None:
+        if getattr(self, "_h", None):
+            lib.msvh_packed_free(self._h)
+            self._h = None
+
+
+class MSV_HMM:
+    """algorithms/MSV_HMM.hpp:17-24 plus the batch entry point this implementation adds."""
+
+    def __init__(self, base_hmm: Profile_HMM, device: int = 0) -> None:
+        self._h = lib.msvh_msv_create(base_hmm._h, device)
+        if not self._h:
+            _raise(-1)
+        self.model_length = int(lib.msvh_msv_length(self._h))
+
+    def run_on_sequence(self, seq: str) -> np.float32:
+        out = C.c_float()
+        status = lib.msvh_msv_run_on_sequence(self._h, seq.encode("latin-1"), C.byref(out))
+        if status:
+            _raise(status)
+        return np.float32(out.value)
+
+    def parallel_run_on_sequence(self, seq: str, should_specialize: bool = False) -> np.float32:
+        out = C.c_float()
+        status = lib.msvh_msv_parallel_run_on_sequence(self._h, seq.encode("latin-1"), int(should_specialize), C.byref(out))
+        if status:
+            _raise(status)
+        return np.float32(out.value)
+
+    def parallel_run_on_sequences(self, database) -> np.ndarray:
+        if isinstance(database, FASTA_protein_sequences):
+            database = Packed_sequences.from_fasta(database)
+        out = np.empty(max(len(database), 1), np.float32)
+        status = lib.msvh_msv_parallel_run_on_packed(self._h, database._h, out)
+        if status:
+            _raise(status)
+        return out[: len(database)]
+
+    def __del__(self) -> None:
+        if getattr(self, "_h", None):
+            lib.msvh_msv_free(self._h)
+            self._h = None

@@ -1,0 +1,103 @@
+#include "MSV_HMM.hpp"
+
+#include <limits>
+#include <stdexcept>
+
+#include "msv_cuda.h"
+
+namespace {
+
+[[noreturn]] void throw_last_error(const char* what, int status) {
+    const auto message = std::string(what) + ": " + msv_cuda_last_error();
+    if (status == MSV_ERR_BAD_RESIDUE) throw std::out_of_range(message);
+    throw std::runtime_error(message);
+}
+
+} // namespace
+
+// Model preparation.  All fp32 expressions (log-odds table, B->M_k, E->C, E->J) are evaluated by the shared host
+// helpers of the C ABI so that the C++ class and every other binding produce the same bits as the reference
+// constructor (reference MSV_HMM.cpp:35-53).
+MSV_HMM::MSV_HMM(const Profile_HMM& base_hmm) : model_length(base_hmm.model_length) {
+    emission_scores.resize(NUM_OF_AMINO_ACIDS * model_length);
+    if (model_length > 0) {
+        msv_host_emission_table(base_hmm.match_emissions.front().data(), model_length, emission_scores.data());
+    }
+    msv_host_model_transitions(model_length, &tr_B_Mk, &tr_E_C, &tr_E_J);
+}
+
+void MSV_HMM::set_device(int device) {
+    device_index = device;
+    device_model.reset();
+}
+
+msv_model* MSV_HMM::on_device() {
+    if (!device_model) {
+        msv_model* raw = nullptr;
+        const auto status =
+            msv_cuda_model_create(emission_scores.data(), model_length, tr_B_Mk, tr_E_C, tr_E_J, device_index, &raw);
+        if (status != MSV_OK) throw_last_error("MSV_HMM: cannot create the device model", status);
+        device_model = std::shared_ptr<msv_model>(raw, [](msv_model* m) { msv_cuda_model_destroy(m); });
+    }
+    return device_model.get();
+}
+
+// Host recurrence (the API's sequential entry point; semantics of reference MSV_HMM.cpp:74-113).  One row of M
+// values is updated in place from the last column to the first, so each cell still reads the previous row's left
+// neighbour; E, J, C, N, B are scalars.  Same operands, same fp32 adds, exact max => same bits as the reference.
+Log_score MSV_HMM::run_on_sequence(const Protein_sequence& seq) {
+    constexpr auto minus_infinity = -std::numeric_limits<Log_score>::infinity();
+    const auto residues = seq.empty() ? size_t(0) : seq.size() - 1; // seq[0] is the '#' sentinel
+    auto codes = std::vector<uint8_t>(residues);
+    if (msv_host_encode(seq.data() + (seq.empty() ? 0 : 1), residues, codes.data(), nullptr) != MSV_OK)
+        throw_last_error("MSV_HMM::run_on_sequence", MSV_ERR_BAD_RESIDUE);
+
+    Log_score tr_loop, tr_move;
+    msv_host_length_transitions(residues, &tr_loop, &tr_move);
+
+    auto row = std::vector<Log_score>(model_length ? model_length : 1, minus_infinity);
+    auto J = minus_infinity, C = minus_infinity;
+    auto N = Log_score(0), B = tr_move;
+    for (const auto code : codes) {
+        const auto* emission = emission_scores.data() + static_cast<size_t>(code) * model_length;
+        const auto entry = B + tr_B_Mk;
+        auto E = minus_infinity;
+        for (auto k = model_length; k-- > 1;) {
+            const auto best_in = row[k - 1] < entry ? entry : row[k - 1];
+            const auto cell = emission[k] + best_in;
+            row[k] = cell;
+            if (E < cell) E = cell;
+        }
+        const auto J_stay = J + tr_loop, J_from_E = E + tr_E_J;
+        J = J_stay < J_from_E ? J_from_E : J_stay;
+        const auto C_stay = C + tr_loop, C_from_E = E + tr_E_C;
+        C = C_stay < C_from_E ? C_from_E : C_stay;
+        N = N + tr_loop;
+        const auto B_from_N = N + tr_move, B_from_J = J + tr_move;
+        B = B_from_N < B_from_J ? B_from_J : B_from_N;
+    }
+    return C + tr_move;
+}
+
+Log_score MSV_HMM::parallel_run_on_sequence(const Protein_sequence& seq, bool /*should_specialize*/) {
+    const auto residues = seq.empty() ? size_t(0) : seq.size() - 1;
+    auto codes = std::vector<uint8_t>(residues);
+    if (msv_host_encode(seq.data() + (seq.empty() ? 0 : 1), residues, codes.data(), nullptr) != MSV_OK)
+        throw_last_error("MSV_HMM::parallel_run_on_sequence", MSV_ERR_BAD_RESIDUE);
+    auto score = Log_score(0);
+    const auto status = msv_cuda_score_sequence(on_device(), codes.data(), residues, &score);
+    if (status != MSV_OK) throw_last_error("MSV_HMM::parallel_run_on_sequence", status);
+    return score;
+}
+
+std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Packed_sequences& database) {
+    auto scores = std::vector<Log_score>(database.size());
+    const auto status = msv_cuda_score_batch(on_device(), database.residues.data(), database.offsets.data(), database.size(),
+                                             scores.data());
+    if (status != MSV_OK) throw_last_error("MSV_HMM::parallel_run_on_sequences", status);
+    return scores;
+}
+
+std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Protein_sequences& sequences) {
+    return parallel_run_on_sequences(Packed_sequences::from_sequences(sequences));
+}

@@ -1,0 +1,66 @@
+#pragma once
+// MSV_HMM -- Multiple Segment Viterbi scoring of protein sequences against a profile HMM, B200 edition.
+//
+// Drop-in for the reference's algorithms/MSV_HMM.hpp:9-24: same aliases, same class name, same three public entry
+// points with the same argument meaning, so test_MSV.cpp, benchmark_MSV.cpp and benchmark_MSV_1400.cpp compile and
+// run unchanged.  What is underneath is new:
+//   * parallel_run_on_sequence() no longer builds an OpenCL context, JIT-compiles kernels and issues 13 launches per
+//     residue (reference MSV_HMM.cpp:287-423); it calls the sm_100a CUDA library through the C ABI in
+//     include/msv_cuda.h (one launch per call).  There is no CPU fallback: without a B200 it throws.
+//   * parallel_run_on_sequences() (new) scores a whole database in one launch -- the throughput entry point.
+//   * `should_specialize` is kept for source compatibility.  The reference used it to pick JIT-specialised kernels,
+//     which silently changed the arithmetic (constants rounded to 6 decimals, MSV_HMM.cpp:325-336).  Here every model
+//     always runs a kernel specialised (at compile time) for its geometry, and both values of the flag return the
+//     same bit-exact fp32 score.
+//   * the object is cheap to copy and move (benchmark_MSV.cpp:35-36 stores it in a growing vector): the device-side
+//     model is shared between copies and released with the last one.
+
+#include <cstddef>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "FASTA_protein_sequences.hpp"
+#include "Packed_sequences.hpp"
+#include "Profile_HMM.hpp"
+
+using Log_score = float;
+
+template <int N> using Log_scores_array = std::array<Log_score, N>;
+template <int N> using Log_scores_arrays_vector = std::vector<Log_scores_array<N>>;
+
+using Kernels_source_code = std::string; // kept for source compatibility; kernels are compiled in, nothing is read at run time
+
+struct msv_model; // opaque device model of the C ABI
+
+class MSV_HMM {
+  public:
+    explicit MSV_HMM(const Profile_HMM& base_hmm);
+
+    // CPU entry point of the API: scalar fp32 recurrence on the host (one rolling row).
+    Log_score run_on_sequence(const Protein_sequence& seq);
+
+    // GPU entry point of the API: one sequence, synchronous.
+    Log_score parallel_run_on_sequence(const Protein_sequence& seq, bool should_specialize = false);
+
+    // GPU, whole database in one launch; scores come back in input order.
+    std::vector<Log_score> parallel_run_on_sequences(const Protein_sequences& sequences);
+    std::vector<Log_score> parallel_run_on_sequences(const Packed_sequences& database);
+
+    size_t length() const { return model_length; } // LENG + 1
+    int device() const { return device_index; }
+    void set_device(int device); // drops the device model; it is re-created lazily on the chosen GPU
+
+  private:
+    size_t model_length;
+    std::vector<Log_score> emission_scores; // [NUM_OF_AMINO_ACIDS][model_length], column 0 is the -inf begin column
+
+    Log_score tr_B_Mk; // B -> M_k, uniform entry
+    Log_score tr_E_C;  // E -> C
+    Log_score tr_E_J;  // E -> J
+
+    int device_index = 0;
+    std::shared_ptr<msv_model> device_model; // created on first GPU call, shared by copies
+
+    msv_model* on_device();
+};

@@ -1,0 +1,115 @@
+/*
+ * msv_cuda.h -- C ABI of the B200 (sm_100a) MSV profile-HMM scan.
+ *
+ * This is the drop-in boundary for the one hot path of IvanTyulyandin/HMM_FASTA_Viterbi: everything that
+ * MSV_HMM::parallel_run_on_sequence (reference algorithms/MSV_HMM.cpp:269-430) and its six OpenCL kernels
+ * (algorithms/MSV_kernels.cl:1-65) compute, re-designed as one batched CUDA launch.  Plain pointers and sizes
+ * only; no C++/torch types.  Host bindings (the C++ MSV_HMM class in hmm_fasta_viterbi_b200/host, the ctypes
+ * wrapper in hmm_fasta_viterbi_b200/_cabi.py, the stubs in INTEGRATION.md) sit on top of exactly these symbols.
+ *
+ * Conventions
+ *   - every function returns an int status: MSV_OK (0) or a negative MSV_ERR_* code; the message for the last
+ *     failure on the calling thread is available from msv_cuda_last_error().  Nothing "prints and continues"
+ *     (contrast: check_errors, reference MSV_HMM.cpp:198-203).
+ *   - residues are byte codes 0..19 in the order A C D E F G H I K L M N P Q R S T V W Y
+ *     (reference MSV_HMM.cpp:29-31); a sequence has NO '#' sentinel here.
+ *   - a database is the concatenation of all sequences plus a uint64 offsets array of n+1 entries
+ *     (sequence q = residues[offsets[q] .. offsets[q+1]) ).
+ *   - scores are fp32 and bit-identical to MSV_HMM::run_on_sequence (reference MSV_HMM.cpp:74-113).
+ *   - there is no CPU fallback: without a CUDA device every msv_cuda_* call fails with MSV_ERR_NO_DEVICE.
+ */
+#ifndef MSV_CUDA_H
+#define MSV_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSV_CUDA_ABI_VERSION 1
+#define MSV_ALPHABET 20
+
+enum {
+    MSV_OK = 0,
+    MSV_ERR_INVALID_ARGUMENT = -1,
+    MSV_ERR_NO_DEVICE = -2,
+    MSV_ERR_CUDA = -3,
+    MSV_ERR_BAD_RESIDUE = -4,      /* a residue code >= 20 (reference: std::out_of_range from .at(), MSV_HMM.cpp:101,383) */
+    MSV_ERR_MODEL_TOO_LONG = -5,
+    MSV_ERR_OUT_OF_MEMORY = -6
+};
+
+typedef struct msv_model msv_model; /* device-resident model: emission table in kernel layout + transition scores */
+typedef struct msv_db msv_db;       /* device-resident packed sequence database, bucketed longest-first */
+
+int msv_cuda_abi_version(void);
+const char* msv_cuda_last_error(void);
+int msv_cuda_device_count(int* count);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Host-side model arithmetic.  Every transcendental of the path is evaluated on the HOST with the same fp32
+ * expressions and the same libm as the reference, and shipped to the device as data; the device only adds and
+ * takes maxima.  These helpers are the single implementation all host bindings share.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* table[j * model_length + i] = logf(match[i * 20 + j] / background[j])     (reference MSV_HMM.cpp:38-45) */
+int msv_host_emission_table(const float* match_emissions, size_t model_length, float* table);
+/* tr_B_Mk = logf(2 / float(model_length * (model_length + 1))), tr_E_C = tr_E_J = logf(1/2)   (MSV_HMM.cpp:47-53) */
+int msv_host_model_transitions(size_t model_length, float* tr_B_Mk, float* tr_E_C, float* tr_E_J);
+/* tr_loop = logf(L / float(L + 3)), tr_move = logf(3 / float(L + 3))                          (MSV_HMM.cpp:59-64) */
+int msv_host_length_transitions(size_t residues, float* tr_loop, float* tr_move);
+/* letters -> codes; returns MSV_OK or MSV_ERR_BAD_RESIDUE (and the offending position in *bad_at if not NULL) */
+int msv_host_encode(const char* letters, size_t n, uint8_t* codes, size_t* bad_at);
+/* Cut n sequences into `parts` contiguous slices of (nearly) equal residue count, i.e. equal DP cell count for a
+ * fixed model: slice p = sequences [bounds[p], bounds[p+1]).  `bounds` has parts+1 entries.  Used to shard a
+ * database over GPUs / ranks. */
+int msv_host_partition_by_cells(const uint64_t* offsets, size_t n, int parts, size_t* bounds);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Model.  Replaces the per-call context + JIT + 20 emission buffers of the reference (MSV_HMM.cpp:287-340).
+ *   emission_scores : [20][model_length] fp32, row stride model_length, column 0 = dummy M0 (= -inf),
+ *                     exactly the layout of MSV_HMM::emission_scores (MSV_HMM.hpp:27-28, MSV_HMM.cpp:43)
+ *   model_length    : LENG + 1 (reference Profile_HMM.cpp:70)
+ * The table is re-laid out for the kernel ([residue][column-quad][lane][4], -inf padded) and kept in HBM; each
+ * CTA stages it into shared memory with one bulk-async (TMA) copy.
+ * ------------------------------------------------------------------------------------------------------------- */
+int msv_cuda_model_create(const float* emission_scores, size_t model_length, float tr_B_Mk, float tr_E_C, float tr_E_J,
+                          int device, msv_model** out);
+int msv_cuda_model_destroy(msv_model* model);
+/* kernel geometry chosen for this model: lanes per sequence (8/16/32), columns per lane, threads per CTA,
+ * dynamic shared memory bytes.  Any pointer may be NULL. */
+int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane, int* threads_per_cta,
+                            size_t* shared_bytes);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Database (device resident).  Uploads residues + offsets, validates the codes, computes the per-length
+ * tr_loop/tr_move table on the host, and buckets the sequences longest-first on the device.
+ * `residues`/`offsets` are HOST pointers and may be freed after the call.
+ * ------------------------------------------------------------------------------------------------------------- */
+int msv_cuda_db_create(int device, const uint8_t* residues, const uint64_t* offsets, size_t n, msv_db** out);
+int msv_cuda_db_destroy(msv_db* db);
+int msv_cuda_db_info(const msv_db* db, size_t* n, uint64_t* total_residues, uint64_t* longest);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Scoring.  One kernel launch scores the whole database.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* resident path: scores_device is a DEVICE pointer to n floats (original sequence order); asynchronous on
+ * `cuda_stream` (a cudaStream_t passed as void*, NULL = default stream). */
+int msv_cuda_db_score_device(msv_model* model, msv_db* db, float* scores_device, void* cuda_stream);
+/* resident database, host result: synchronous, copies n floats into scores_host. */
+int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host);
+/* end-to-end path with HOST buffers in and out: upload + bucket + scan + download in one synchronous call.
+ * This is what MSV_HMM::parallel_run_on_sequences (the batch entry point the C++ class adds) calls. */
+int msv_cuda_score_batch(msv_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host);
+/* one sequence, synchronous: the body of MSV_HMM::parallel_run_on_sequence (reference MSV_HMM.cpp:269-430). */
+int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score);
+
+/* kernel launches issued by this library on the calling thread since the last reset (for bench.py's gpu_launches) */
+uint64_t msv_cuda_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSV_CUDA_H */

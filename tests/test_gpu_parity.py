@@ -1,0 +1,215 @@
+"""GPU parity tests proper (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(include/msv_cuda.h), either directly (hmm_fasta_viterbi_b200._cabi) or via the C++ MSV_HMM class that sits on it.
+The bar is bit-exact fp32 (tolerance 0 ULP): each cell performs the reference's add on the reference's operands, and
+max is exact, so any difference is a bug."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import hmm_fasta_viterbi_b200 as msv
+from conftest import REPO, fasta_path, hmm_path, model_files
+from hmm_fasta_viterbi_b200 import _cabi
+from oracle_lib import LETTERS, pack
+
+pytestmark = pytest.mark.gpu
+CORES = os.cpu_count() or 1
+
+
+def ubits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def bits(x) -> str:
+    return format(int(np.float32(x).view(np.uint32)), "08x")
+
+
+def device_model(oracle, name, device=0):
+    h = oracle.load_hmm(hmm_path(name))
+    table, tr3 = oracle.prepare(h["match_emissions"])
+    mine = _cabi.emission_table(h["match_emissions"])
+    assert ubits(mine).tolist() == ubits(table).tolist()
+    return msv.Model(mine, *_cabi.model_transitions(h["model_length"]), device=device), table, tr3
+
+
+def random_db(rng, n, lo, hi, background=None):
+    lens = rng.integers(lo, hi + 1, size=n)
+    if background is None:
+        seqs = [rng.integers(0, 20, size=int(k), dtype=np.uint8) for k in lens]
+    else:
+        seqs = [rng.choice(20, size=int(k), p=background).astype(np.uint8) for k in lens]
+    return seqs, *pack(seqs)
+
+
+# ---- configuration 1 and 2 inputs: every fixture model against the committed reference bits ---------------------
+@pytest.mark.parametrize("name", model_files())
+def test_golden_scores_single_sequence_api(golden_scores, golden_readers, name):
+    """MSV_HMM::parallel_run_on_sequence (reference MSV_HMM.hpp:23), both values of should_specialize."""
+    model = msv.MSV_HMM(msv.Profile_HMM(hmm_path(name)))
+    g = golden_scores["scores"][name]
+    seqs = {"example": golden_readers["fasta"]["fasta_like_example.fsa"], "random": golden_readers["fasta"]["random_FASTA.fsa"],
+            "extra": golden_scores["meta"]["extra_sequences"]}
+    for key, want in g.items():
+        assert [bits(model.parallel_run_on_sequence(s)) for s in seqs[key]] == want, (name, key)
+        assert [bits(model.parallel_run_on_sequence(s, True)) for s in seqs[key]] == want, (name, key, "specialised")
+    # the batch entry point returns the same bits in input order
+    everything = seqs["example"] + seqs["random"] + seqs["extra"]
+    packed = msv.Packed_sequences.from_arrays(*pack([np.array([LETTERS.index(c) for c in s[1:]], np.uint8) for s in everything]))
+    got = model.parallel_run_on_sequences(packed)
+    assert [bits(v) for v in got] == g["example"] + g["random"] + g["extra"]
+    # seq (host) == par (device), the invariant of the reference's test_MSV.cpp:26 with tolerance 0
+    assert [bits(model.run_on_sequence(s)) for s in seqs["example"]] == g["example"]
+
+
+# ---- batches against the oracle -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n,hi", [("100.hmm", 6000, 400), ("500.hmm", 3000, 400), ("1001.hmm", 1500, 400),
+                                        ("1400.hmm", 1500, 500), ("2405.hmm", 800, 500)])
+def test_batch_matches_oracle(oracle, name, n, hi):
+    model, table, tr3 = device_model(oracle, name)
+    rng = np.random.default_rng(int(name.split(".")[0]))
+    seqs, codes, offsets = random_db(rng, n, 0, hi)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    got = model.score_batch(codes, offsets)
+    assert ubits(got).tolist() == ubits(want).tolist()
+    # resident database path gives the same bits, twice (the work queue is reset between launches)
+    db = msv.Database(codes, offsets)
+    assert db.info() == {"n": n, "total_residues": int(offsets[-1]), "longest": int(np.diff(offsets.astype(np.int64)).max())}
+    assert ubits(db.score(model)).tolist() == ubits(want).tolist()
+    assert ubits(db.score(model)).tolist() == ubits(want).tolist()
+
+
+def test_homologous_sequences_exercise_the_J_state(oracle):
+    """Sequences sampled from the model itself score high and make J (multi-hit) win over N in B (MSV_HMM.cpp:110)."""
+    name = "300.hmm"
+    model, table, tr3 = device_model(oracle, name)
+    h = oracle.load_hmm(hmm_path(name))
+    rng = np.random.default_rng(5)
+    cons = h["match_emissions"][1:].argmax(axis=1).astype(np.uint8)
+    seqs = []
+    for _ in range(200):
+        a, b = sorted(rng.integers(0, len(cons), size=2))
+        noise = rng.integers(0, 20, size=int(rng.integers(0, 50)), dtype=np.uint8)
+        seqs.append(np.concatenate([noise, cons[a:b], noise[::-1], cons[a // 2:b]]))
+    codes, offsets = pack(seqs)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    assert (want > 0).sum() > 50
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+
+
+@pytest.mark.parametrize("geometry", ["8,4", "8,16", "8,64", "16,8", "16,32", "16,88", "32,4", "32,20", "32,24", "32,44",
+                                       "32,56", "32,60", "32,88"])
+def test_every_kernel_geometry(oracle, geometry, monkeypatch):
+    """Lanes-per-sequence x columns-per-lane variants, forced through MSV_CUDA_GEOMETRY, all give reference bits."""
+    G, K = (int(v) for v in geometry.split(","))
+    fits = [n for n in model_files() if int(n.split(".")[0]) <= G * K]
+    name = fits[-1] if fits else None
+    if name is None:
+        pytest.skip("no fixture model fits this geometry")
+    monkeypatch.setenv("MSV_CUDA_GEOMETRY", geometry)
+    model, table, tr3 = device_model(oracle, name)
+    assert model.geometry["lanes_per_sequence"] == G and model.geometry["columns_per_lane"] == K
+    rng = np.random.default_rng(G * 1000 + K)
+    n = max(64, min(4000, int(4e7 / (int(name.split(".")[0]) * 150))))
+    seqs, codes, offsets = random_db(rng, n, 0, 300)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+
+
+def test_all_models_default_geometry_small_batch(oracle):
+    rng = np.random.default_rng(11)
+    seqs, codes, offsets = random_db(rng, 300, 0, 200)
+    for name in model_files():
+        model, table, tr3 = device_model(oracle, name)
+        want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+        assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist(), name
+
+
+# ---- edge cases --------------------------------------------------------------------------------------------------
+def test_edge_cases(oracle):
+    model, table, tr3 = device_model(oracle, "1400.hmm")
+    # empty database
+    assert model.score_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64)).size == 0
+    # only empty sequences: score is -inf (tr_loop = log(0) = -inf, MSV_HMM.cpp:59-64)
+    got = model.score_batch(np.zeros(0, np.uint8), np.zeros(6, np.uint64))
+    assert np.isneginf(got).all() and got.size == 5
+    # one residue, and ragged mixtures with empties in between
+    seqs = [np.array([3], np.uint8), np.zeros(0, np.uint8), np.arange(20, dtype=np.uint8), np.zeros(0, np.uint8),
+            np.full(1000, 19, np.uint8), np.array([0, 19], np.uint8)]
+    codes, offsets = pack(seqs)
+    want = oracle.score_batch(table, tr3, codes, offsets)
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+    assert bits(model.score_sequence(seqs[4])) == bits(want[4])
+    assert np.isneginf(model.score_sequence(np.zeros(0, np.uint8)))
+
+
+def test_bad_residue_code_is_reported_not_scored(oracle):
+    model, _, _ = device_model(oracle, "100.hmm")
+    codes = np.array([1, 2, 3, 20, 4], np.uint8)
+    with pytest.raises(_cabi.MsvCudaError) as err:
+        model.score_batch(codes, np.array([0, 5], np.uint64))
+    assert err.value.status == _cabi.MSV_ERR_BAD_RESIDUE and "position 3" in str(err.value)
+    with pytest.raises(_cabi.MsvCudaError):
+        msv.Database(np.array([255], np.uint8), np.array([0, 1], np.uint64))
+    with pytest.raises(_cabi.MsvCudaError):
+        model.score_batch(codes, np.array([0, 3, 2], np.uint64))  # non-monotonic offsets
+    with pytest.raises(KeyError):
+        msv.MSV_HMM(msv.Profile_HMM(hmm_path("100.hmm"))).parallel_run_on_sequence("#ACDZ")
+
+
+def test_long_sequence_and_misaligned_offsets(oracle):
+    """One titin-like sequence (config 5 shape, shortened) plus neighbours that start at every byte alignment."""
+    model, table, tr3 = device_model(oracle, "2405.hmm")
+    rng = np.random.default_rng(2405)
+    seqs = [rng.integers(0, 20, size=k, dtype=np.uint8) for k in (1, 2, 3, 5, 12001, 7, 1, 6, 9, 4)]
+    codes, offsets = pack(seqs)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+
+
+# ---- size-independent properties at BASELINE sizes ----------------------------------------------------------------
+def test_full_size_properties_config4(oracle):
+    """1400.hmm x 1M synthetic sequences (config 4): permutation equivariance, duplicate consistency, run-to-run
+    determinism, and a seeded sample checked against the oracle."""
+    model, table, tr3 = device_model(oracle, "1400.hmm")
+    db = msv.Packed_sequences.synthetic_swissprot_like(1_000_000, 20261018)
+    codes, offsets = db.residues, db.offsets
+    first = model.score_batch(codes, offsets)
+    second = msv.Database(codes, offsets).score(model)
+    assert (ubits(first) == ubits(second)).all()
+    assert np.isfinite(first).all()
+    rng = np.random.default_rng(4)
+    sample = rng.choice(len(db), size=400, replace=False)
+    seqs = [codes[int(offsets[q]):int(offsets[q + 1])] for q in sample]
+    sc, so = pack(seqs)
+    want = oracle.score_batch(table, tr3, sc, so, threads=CORES)
+    assert ubits(first[sample]).tolist() == ubits(want).tolist()
+    # a reversed copy of a slice scores identically, sequence by sequence
+    sl = np.arange(200_000, 230_000)[::-1]
+    rc, ro = pack([codes[int(offsets[q]):int(offsets[q + 1])] for q in sl])
+    assert (ubits(model.score_batch(rc, ro)) == ubits(first[sl])).all()
+
+
+def test_full_size_properties_config5(oracle):
+    """2405.hmm x long sequences (config 5 shape, 256 sequences): determinism and a sample against the oracle."""
+    model, table, tr3 = device_model(oracle, "2405.hmm")
+    db = msv.Packed_sequences.synthetic_long_uniform(256, 2405, 10_000, 35_000)
+    codes, offsets = db.residues, db.offsets
+    first = model.score_batch(codes, offsets)
+    assert (ubits(first) == ubits(model.score_batch(codes, offsets))).all()
+    sample = [0, 17, 255]
+    sc, so = pack([codes[int(offsets[q]):int(offsets[q + 1])] for q in sample])
+    want = oracle.score_batch(table, tr3, sc, so, threads=CORES)
+    assert ubits(first[sample]).tolist() == ubits(want).tolist()
+
+
+# ---- the reference's own programs, unchanged, against this implementation -----------------------------------------
+@pytest.mark.parametrize("prog,cwd", [("test_hmm_parsing", "data_readers"), ("test_fasta_parsing", "data_readers"),
+                                       ("test_MSV", "algorithms"), ("benchmark_MSV_1400", "algorithms")])
+def test_reference_programs_run_unchanged(prog, cwd):
+    exe = os.path.join(REPO, "build", cwd, prog)
+    if not os.path.exists(exe):
+        pytest.skip("build/ not populated (tools/build_reference_programs.sh needs /root/reference at build time)")
+    run = subprocess.run([exe], cwd=os.path.join(REPO, "build", cwd), capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "failed" not in run.stdout
