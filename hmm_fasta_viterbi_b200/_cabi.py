@@ -65,7 +65,7 @@ lib.msv_host_partition_by_cells.argtypes = [_u64, C.c_size_t, C.c_int, C.POINTER
 lib.msv_cuda_model_create.argtypes = [_f32, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_void_p)]
 lib.msv_cuda_model_destroy.argtypes = [C.c_void_p]
 lib.msv_cuda_model_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
-                                        C.POINTER(C.c_size_t)]
+                                        C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
 lib.msv_cuda_db_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
 lib.msv_cuda_db_destroy.argtypes = [C.c_void_p]
 lib.msv_cuda_db_info.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -160,10 +160,10 @@ class Model:
 
     @property
     def geometry(self) -> dict:
-        g, k, t, s = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
-        check(lib.msv_cuda_model_geometry(self.handle, C.byref(g), C.byref(k), C.byref(t), C.byref(s)))
-        return {"lanes_per_sequence": g.value, "columns_per_lane": k.value, "threads_per_cta": t.value,
-                "shared_bytes": s.value}
+        g, k, kt, t, s = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        check(lib.msv_cuda_model_geometry(self.handle, C.byref(g), C.byref(k), C.byref(kt), C.byref(t), C.byref(s)))
+        return {"lanes_per_sequence": g.value, "columns_per_lane": k.value, "tensor_columns_per_lane": kt.value,
+                "threads_per_cta": t.value, "shared_bytes": s.value}
 
     def score_batch(self, residues, offsets, out=None) -> np.ndarray:
         """End-to-end call with host buffers (numpy arrays or pinned torch tensors)."""

@@ -46,45 +46,76 @@ int fail(int code, const char* fmt, ...) {
         }                                                                                                              \
     } while (0)
 
-// ---- kernel registry: one instantiation per (lanes per sequence, columns per lane) ---------------------------------
+// ---- kernel registry ------------------------------------------------------------------------------------------------
+// Two kernel families (msv_kernels.cuh):
+//   generic : G = 8/16/32 lanes per sequence, whole table in shared memory           (KT = -1 below)
+//   warp    : G = 32, table split between shared memory and KT tensor-memory columns per lane (KT = 0, 8, 16, 24)
 constexpr int threads_for(int K) { return K <= 20 ? 1024 : K <= 40 ? 768 : K <= 56 ? 640 : 512; }
+constexpr int warp_threads_for(int K, int KT) { return K + (KT > 0 ? 8 : 0) <= 24 ? 1024 : K <= 28 ? 768 : K <= 36 ? 640 : 512; }
 
 using Scan_kernel = void (*)(const msv::Scan_params);
 struct Geometry {
-    int G, K, threads;
-    Scan_kernel fn;
+    int G, K, KT, threads;
+    Scan_kernel fn;         // general transitions
+    Scan_kernel fn_cj_same; // tr_E_C == tr_E_J bitwise (C is J); same as fn for the generic family
+    size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET) * (K - std::max(KT, 0)) * G * sizeof(float); }
 };
 
-template <int G, int K> constexpr Geometry geometry_entry() { return Geometry{G, K, threads_for(K), msv::msv_scan_kernel<G, K, threads_for(K)>}; }
+template <int G, int K> constexpr Geometry generic_entry() {
+    return Geometry{G, K, -1, threads_for(K), msv::msv_scan_kernel<G, K, threads_for(K)>, msv::msv_scan_kernel<G, K, threads_for(K)>};
+}
+template <int K, int KT> constexpr Geometry warp_entry() {
+    return Geometry{32, K, KT, warp_threads_for(K, KT), msv::msv_scan_warp_kernel<K, KT, warp_threads_for(K, KT), false>,
+                    msv::msv_scan_warp_kernel<K, KT, warp_threads_for(K, KT), true>};
+}
 
-#define MSV_FOR_EACH_K(X, G)                                                                                           \
-    X(G, 4) X(G, 8) X(G, 12) X(G, 16) X(G, 20) X(G, 24) X(G, 28) X(G, 32) X(G, 36) X(G, 40) X(G, 44) X(G, 48) X(G, 52)  \
-    X(G, 56) X(G, 60) X(G, 64) X(G, 68) X(G, 72) X(G, 76) X(G, 80) X(G, 84) X(G, 88)
-#define MSV_ENTRY(G, K) geometry_entry<G, K>(),
-const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_ENTRY, 8) MSV_FOR_EACH_K(MSV_ENTRY, 16) MSV_FOR_EACH_K(MSV_ENTRY, 32)};
+template <int K, int KT, int T> constexpr Geometry warp_entry_threads() {
+    return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false>, msv::msv_scan_warp_kernel<K, KT, T, true>};
+}
 
-const Geometry* find_geometry(int G, int K) {
+#define MSV_FOR_EACH_K(X, A)                                                                                           \
+    X(A, 4) X(A, 8) X(A, 12) X(A, 16) X(A, 20) X(A, 24) X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52)  \
+    X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) X(A, 76) X(A, 80) X(A, 84) X(A, 88)
+#define MSV_FOR_EACH_K_FROM_24(X, A)                                                                                   \
+    X(A, 24) X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) \
+    X(A, 76) X(A, 80) X(A, 84) X(A, 88)
+#define MSV_GENERIC(G, K) generic_entry<G, K>(),
+#define MSV_WARP(KT, K) warp_entry<K, KT>(),
+const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(MSV_GENERIC, 16) MSV_FOR_EACH_K(MSV_GENERIC, 32)
+                                     MSV_WARP(0, 4) MSV_WARP(0, 8) MSV_WARP(8, 8) MSV_WARP(8, 12) MSV_WARP(8, 16) MSV_WARP(8, 20)
+                                         MSV_FOR_EACH_K_FROM_24(MSV_WARP, 16) MSV_WARP(0, 44) MSV_WARP(8, 44) MSV_WARP(24, 44)
+                                             warp_entry_threads<44, 16, 640>(), warp_entry_threads<44, 16, 448>(),
+                                 warp_entry_threads<44, 16, 384>()};
+
+const Geometry* find_geometry(int G, int K, int KT, int threads = 0) {
     for (const auto& g : g_geometries)
-        if (g.G == G && g.K == K) return &g;
+        if (g.G == G && g.K == K && g.KT == KT && (threads == 0 || g.threads == threads)) return &g;
     return nullptr;
 }
 
 int round_up4(size_t v) { return static_cast<int>((v + 3) / 4 * 4); }
 
 // Fewer lanes per sequence amortise the per-row bookkeeping over more cells, as long as the row still fits a lane's
-// registers; MSV_CUDA_GEOMETRY="G,K" overrides the choice (tuning aid).
+// registers.  Models that need a whole warp per sequence use the shared-memory + tensor-memory split; that kernel
+// needs the last column of lane 31 to be padding, hence 32*K > columns there.
+// MSV_CUDA_GEOMETRY="G,K[,KT]" overrides the choice (tuning aid; without KT the generic kernel is selected).
 const Geometry* choose_geometry(size_t columns) {
     if (const char* env = std::getenv("MSV_CUDA_GEOMETRY")) {
-        int G = 0, K = 0;
-        if (std::sscanf(env, "%d,%d", &G, &K) == 2 && static_cast<size_t>(G) * K >= columns)
-            if (const Geometry* g = find_geometry(G, K)) return g;
+        int G = 0, K = 0, KT = -1, T = 0;
+        const int got = std::sscanf(env, "%d,%d,%d,%d", &G, &K, &KT, &T);
+        if (got == 2 && static_cast<size_t>(G) * K >= columns)
+            if (const Geometry* g = find_geometry(G, K, -1)) return g;
+        if (got >= 3 && static_cast<size_t>(G) * K > columns)
+            if (const Geometry* g = find_geometry(G, K, KT, T)) return g;
     }
     constexpr int preferred_K = 64;
-    for (int G : {8, 16, 32}) {
+    for (int G : {8, 16}) {
         const int K = std::max(4, round_up4((columns + G - 1) / G));
-        if (K <= preferred_K || (G == 32 && K <= msv::kMaxColumnsPerLane)) return find_geometry(G, K);
+        if (K <= preferred_K) return find_geometry(G, K, -1);
     }
-    return nullptr;
+    const int K = std::max(4, round_up4((columns + 1 + 31) / 32)); // 32*K > columns
+    if (K > msv::kMaxColumnsPerLane) return nullptr;
+    return find_geometry(32, K, K >= 24 ? 16 : K >= 12 ? 8 : 0);
 }
 
 struct Device_guard {
@@ -126,7 +157,8 @@ struct msv_model {
     int device = 0;
     size_t model_length = 0;
     const Geometry* geo = nullptr;
-    size_t table_bytes = 0;
+    size_t table_bytes = 0;  // whole table in HBM (shared-memory part followed by tensor-memory part)
+    size_t shared_bytes = 0; // dynamic shared memory of the scan kernel
     float4* d_table = nullptr;
     float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
     int sm_count = 0;
@@ -277,7 +309,7 @@ int launch_scan(msv_model* model, msv_db* db, float* d_scores, cudaStream_t stre
     p.scores = d_scores;
     p.queue_head = db->d_queue;
     p.n = static_cast<uint32_t>(db->n);
-    p.table_bytes = static_cast<uint32_t>(model->table_bytes);
+    p.table_bytes = static_cast<uint32_t>(model->shared_bytes);
     p.tr_by_sequence = 0;
     p.tr_B_Mk = model->tr_B_Mk;
     p.tr_E_C = model->tr_E_C;
@@ -291,7 +323,8 @@ int launch_scan(msv_model* model, msv_db* db, float* d_scores, cudaStream_t stre
         const size_t warps = (db->n * geo->G + 31) / 32;
         threads = static_cast<int>(std::min<size_t>(geo->threads, std::max<size_t>(1, warps) * 32));
     }
-    geo->fn<<<ctas, threads, model->table_bytes, stream>>>(p);
+    const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
+    (cj_same ? geo->fn_cj_same : geo->fn)<<<ctas, threads, model->shared_bytes, stream>>>(p);
     ++g_launches;
     MSV_CUDA_TRY(cudaGetLastError());
     return MSV_OK;
@@ -425,38 +458,49 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         return fail(MSV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major,
                     prop.minor);
 
-    // kernel layout: [residue][quad q][lane g][4], column = g*K + 4q + c + 1, -inf beyond the model
-    const int G = geo->G, K = geo->K;
-    const size_t floats = static_cast<size_t>(MSV_ALPHABET) * K * G;
-    std::vector<float> laid(floats, -std::numeric_limits<float>::infinity());
+    // kernel layout (see msv_kernels.cuh).  Lane g owns model columns g*K + j + 1, j = 0..K-1; -inf beyond the model.
+    //   shared-memory part : [residue][quad q][lane g][4]   j = KT + 4q + c      (generic kernel: KT = 0)
+    //   tensor-memory part : [residue][lane g][KT]          j = 0 .. KT-1        (warp kernel with KT > 0 only)
+    const int G = geo->G, K = geo->K, KT = std::max(geo->KT, 0), KS = K - KT;
+    const size_t shared_floats = static_cast<size_t>(MSV_ALPHABET) * KS * G;
+    const size_t floats = shared_floats + static_cast<size_t>(MSV_ALPHABET) * KT * G;
+    std::vector<float> laid(std::max<size_t>(floats, 4), -std::numeric_limits<float>::infinity());
+    const auto emission = [&](int res, int g, int j) {
+        const size_t col = static_cast<size_t>(g) * K + j + 1;
+        return col <= columns ? emission_scores[res * model_length + col] : -std::numeric_limits<float>::infinity();
+    };
     for (int res = 0; res < MSV_ALPHABET; ++res)
-        for (int q = 0; q < K / 4; ++q)
-            for (int g = 0; g < G; ++g)
-                for (int c = 0; c < 4; ++c) {
-                    const size_t col = static_cast<size_t>(g) * K + 4 * q + c + 1;
-                    if (col <= columns)
-                        laid[((static_cast<size_t>(res) * (K / 4) + q) * G + g) * 4 + c] = emission_scores[res * model_length + col];
-                }
+        for (int g = 0; g < G; ++g) {
+            for (int js = 0; js < KS; ++js)
+                laid[((static_cast<size_t>(res) * (KS / 4) + js / 4) * G + g) * 4 + js % 4] = emission(res, g, KT + js);
+            for (int jt = 0; jt < KT; ++jt)
+                laid[shared_floats + (static_cast<size_t>(res) * G + g) * KT + jt] = emission(res, g, jt);
+        }
 
     auto* model = new (std::nothrow) msv_model();
     if (!model) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
     model->device = device;
     model->model_length = model_length;
     model->geo = geo;
-    model->table_bytes = floats * sizeof(float);
+    model->table_bytes = laid.size() * sizeof(float);
+    model->shared_bytes = geo->shared_bytes();
     model->tr_B_Mk = tr_B_Mk;
     model->tr_E_C = tr_E_C;
     model->tr_E_J = tr_E_J;
     model->sm_count = prop.multiProcessorCount;
-    if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < model->table_bytes + 64) {
+    if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < model->shared_bytes + 64) {
+        const size_t need = model->shared_bytes;
         delete model;
-        return fail(MSV_ERR_MODEL_TOO_LONG, "emission table of %zu bytes exceeds shared memory", floats * sizeof(float));
+        return fail(MSV_ERR_MODEL_TOO_LONG, "emission table of %zu bytes exceeds shared memory", need);
     }
     cudaError_t err = cudaMalloc(&model->d_table, model->table_bytes);
     if (err == cudaSuccess) err = cudaMemcpy(model->d_table, laid.data(), model->table_bytes, cudaMemcpyHostToDevice);
     if (err == cudaSuccess)
         err = cudaFuncSetAttribute(reinterpret_cast<const void*>(geo->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(model->table_bytes));
+                                   static_cast<int>(model->shared_bytes));
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(reinterpret_cast<const void*>(geo->fn_cj_same), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(model->shared_bytes));
     if (err != cudaSuccess) {
         cudaFree(model->d_table);
         delete model;
@@ -478,13 +522,14 @@ int msv_cuda_model_destroy(msv_model* model) {
     return MSV_OK;
 }
 
-int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane, int* threads_per_cta,
-                            size_t* shared_bytes) {
+int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane,
+                            int* tensor_columns_per_lane, int* threads_per_cta, size_t* shared_bytes) {
     if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
     if (lanes_per_sequence) *lanes_per_sequence = model->geo->G;
     if (columns_per_lane) *columns_per_lane = model->geo->K;
+    if (tensor_columns_per_lane) *tensor_columns_per_lane = model->geo->KT;
     if (threads_per_cta) *threads_per_cta = model->geo->threads;
-    if (shared_bytes) *shared_bytes = model->table_bytes;
+    if (shared_bytes) *shared_bytes = model->shared_bytes;
     return MSV_OK;
 }
 

@@ -217,6 +217,241 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
     }
 }
 
+// =====================================================================================================================
+// Warp-per-sequence scan with the emission table split between shared memory and TENSOR MEMORY (TMEM).
+//
+// Why: with one LDS.128 per four cells the generic kernel above saturates the shared-memory pipe (ncu: 88 % of the
+// LSU wavefront peak at M = 1400) while the fp32 pipes still have head-room.  Blackwell has a second on-chip memory
+// with its own read path: 256 KB of TMEM per SM (512 columns x 128 lanes x 32 bit), read with tcgen05.ld at
+// ~300 B/clk/SM (tools/microbench.cu), i.e. more than twice the 128 B/clk of shared memory.  tcgen05.ld.32x32b.xN gives
+// thread t of a warp N consecutive columns of TMEM lane 32*(warp%4)+t -- exactly "N emissions of my own model columns".
+// So each lane's first KT model columns come from TMEM (column = residue*KT + j, one copy per lane quarter), the other
+// KS = K-KT from shared memory.  The TMEM load for a row is issued first, the shared-memory columns are processed while
+// it is in flight, tcgen05.wait::ld, then the TMEM columns.  The address must be warp-uniform, which is why this
+// variant exists for G == 32 only (all lanes of the warp scan the same residue).
+// =====================================================================================================================
+__device__ __forceinline__ float4 lds128(uint32_t shared_address) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(shared_address));
+    return v;
+}
+
+__device__ __forceinline__ void tmem_store8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]),
+                 "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_load8(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_load16(uint32_t taddr, float* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+          "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr));
+}
+
+// tcgen05.wait::ld; the loaded registers are in/out operands so that no use of them can be scheduled above the wait.
+__device__ __forceinline__ void tmem_wait8(float* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])::"memory");
+}
+__device__ __forceinline__ void tmem_wait16(float* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                   "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])::"memory");
+}
+
+template <int KT> __device__ __forceinline__ void tmem_load(uint32_t taddr, float* v) {
+    static_assert(KT == 8 || KT == 16 || KT == 24, "TMEM columns per lane");
+    if constexpr (KT == 8) tmem_load8(taddr, v);
+    if constexpr (KT == 16) tmem_load16(taddr, v);
+    if constexpr (KT == 24) {
+        tmem_load16(taddr, v);
+        tmem_load8(taddr + 16, v + 16);
+    }
+}
+template <int KT> __device__ __forceinline__ void tmem_wait(float* v) {
+    if constexpr (KT == 8) tmem_wait8(v);
+    if constexpr (KT == 16) tmem_wait16(v);
+    if constexpr (KT == 24) {
+        tmem_wait16(v);
+        tmem_wait8(v + 16); // second wait is free: everything has already landed
+    }
+}
+
+// Table in global memory for this kernel:
+//   [0, 20*KS*128)            shared-memory part  [residue][quad q][lane][4]   column j = KT + 4q + c
+//   [20*KS*128, +20*32*KT*4)  TMEM part           [residue][lane][KT]          column j = 0 .. KT-1
+// (model column of lane l, index j:  l*K + j + 1;  -inf beyond the model)
+//
+// Per-row bookkeeping is trimmed to what the fp32 "ALU" pipe (FMNMX, half rate) can least afford:
+//   * the host guarantees that the last column of lane 31 is padding (32*K > model columns), so that column is -inf
+//     for ever and a ROTATING shuffle hands lane 0 the -inf of column 0 for free (no select);
+//   * when tr_E_C and tr_E_J are the same bits (always, for the reference's nu = 2, MSV_HMM.cpp:49-53) the C and J
+//     recurrences are the same function of the same inputs, so C == J and only J is carried (CJ_SAME);
+//   * one FMNMX3 chain accumulates E; max(N+move, J+move) is computed as max(N, J)+move (rounding is monotone).
+template <int K, int KT, int THREADS, bool CJ_SAME>
+__global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_params p) {
+    static_assert(KT == 0 || KT == 8 || KT == 16 || KT == 24, "TMEM columns per lane");
+    constexpr int KS = K - KT;
+    static_assert(K % 4 == 0 && KS >= 0 && KS % 4 == 0 && K <= kMaxColumnsPerLane, "columns per lane");
+    constexpr uint32_t ROW_BYTES = KS * 32 * 4;
+    constexpr uint32_t SMEM_TABLE_BYTES = kAlphabet * ROW_BYTES;
+    constexpr uint32_t COPY_CHUNK = 32768;
+    constexpr uint32_t TMEM_COLUMNS = 512;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t table_ready;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    // ---- stage the shared-memory part with the TMA unit ----
+    if (threadIdx.x == 0) mbarrier_init(&table_ready, 1);
+    if constexpr (KT > 0) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                         "n"(TMEM_COLUMNS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if constexpr (KT > 0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if constexpr (KS > 0) {
+        if (threadIdx.x == 0) {
+            mbarrier_expect_tx(&table_ready, SMEM_TABLE_BYTES);
+#pragma unroll 1
+            for (uint32_t at = 0; at + 1 <= SMEM_TABLE_BYTES; at += COPY_CHUNK) {
+                const uint32_t bytes = min(COPY_CHUNK, SMEM_TABLE_BYTES - at);
+                tma_bulk_load(smem_raw + at, reinterpret_cast<const unsigned char*>(p.table) + at, bytes, &table_ready);
+            }
+        }
+    }
+    // ---- fill the TMEM part: warps 0..3 each write the copy of their own lane quarter ----
+    uint32_t tmem_lane_base = 0;
+    if constexpr (KT > 0) {
+        tmem_lane_base = tmem_base_slot + ((static_cast<uint32_t>(warp & 3) * 32u) << 16);
+        if (warp < 4) {
+            const float4* src =
+                reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(p.table) + SMEM_TABLE_BYTES);
+            for (int x = 0; x < kAlphabet; ++x) {
+#pragma unroll
+                for (int c = 0; c < KT / 8; ++c) {
+                    const float4 a = __ldg(src + ((x * 32 + lane) * KT + 8 * c) / 4);
+                    const float4 b = __ldg(src + ((x * 32 + lane) * KT + 8 * c) / 4 + 1);
+                    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    tmem_store8(tmem_lane_base + x * KT + 8 * c, v);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if constexpr (KS > 0) mbarrier_wait(&table_ready, 0);
+
+    const uint32_t tab_lane = smem_u32(smem_raw) + lane * 16;
+    const int left_lane = (lane + 31) & 31;
+    const float NEG_INF = __int_as_float(0xff800000);
+    const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
+
+    for (;;) {
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(p.queue_head, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= p.n) break;
+        const uint32_t idx = __ldg(p.order + ticket);
+        const uint64_t begin = __ldg(p.offsets + idx);
+        const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
+        const float2 tr = __ldg(p.length_tr + (p.tr_by_sequence ? idx : len));
+        const float loop = tr.x, move = tr.y;
+
+        float m[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) m[j] = NEG_INF; // MSV_HMM.cpp:86
+        float J = NEG_INF, C = NEG_INF, N = 0.0f, B = move; // MSV_HMM.cpp:96-97
+
+        auto row = [&](const uint32_t x) {
+            float te[KT > 0 ? KT : 1];
+            if constexpr (KT > 0) tmem_load<KT>(tmem_lane_base + x * KT, te);
+            const uint32_t erow = tab_lane + x * ROW_BYTES;
+            const float bt = B + tBMk; // MSV_HMM.cpp:103, B -> M_k entry
+            // lane 0 receives lane 31's last column, which is padding and therefore -inf: the dummy column M0
+            const float left = __shfl_sync(0xffffffffu, m[K - 1], left_lane);
+            float e = NEG_INF;
+#pragma unroll
+            for (int q = KS / 4 - 1; q >= 0; --q) {
+                const float4 ev = lds128(erow + q * 512);
+                const int j = KT + 4 * q;
+                m[j + 3] = ev.w + fmaxf(m[j + 2], bt);
+                m[j + 2] = ev.z + fmaxf(m[j + 1], bt);
+                m[j + 1] = ev.y + fmaxf(m[j], bt);
+                m[j] = ev.x + fmaxf(j ? m[j > 0 ? j - 1 : 0] : left, bt);
+                e = fmaxf(fmaxf(e, m[j + 3]), m[j + 2]); // MSV_HMM.cpp:104
+                e = fmaxf(fmaxf(e, m[j + 1]), m[j]);
+            }
+            if constexpr (KT > 0) {
+                tmem_wait<KT>(te);
+#pragma unroll
+                for (int j = KT - 1; j >= 1; j -= 2) {
+                    m[j] = te[j] + fmaxf(m[j - 1], bt);
+                    m[j - 1] = te[j - 1] + fmaxf(j > 1 ? m[j > 1 ? j - 2 : 0] : left, bt);
+                    e = fmaxf(fmaxf(e, m[j]), m[j - 1]);
+                }
+            }
+            float E;
+            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(E) : "f"(e));
+            J = fmaxf(J + loop, E + tEJ);                           // MSV_HMM.cpp:107
+            if constexpr (!CJ_SAME) C = fmaxf(C + loop, E + tEC);   // MSV_HMM.cpp:108
+            N = N + loop;                                           // MSV_HMM.cpp:109
+            B = fmaxf(N, J) + move; // MSV_HMM.cpp:110: max(N+move, J+move) == max(N, J)+move exactly (rounding is monotone)
+        };
+
+        // residues arrive as aligned 32-bit words (4 per load, one word prefetched ahead); a funnel shift undoes the
+        // byte misalignment of the sequence start
+        const uint32_t shift = (static_cast<uint32_t>(begin) & 3u) * 8u;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues + (begin & ~static_cast<uint64_t>(3)));
+        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        wp += 2;
+        const uint32_t quads = len >> 2;
+#pragma unroll 1
+        for (uint32_t i = 0; i < quads; ++i) {
+            const uint32_t word = __funnelshift_r(w0, w1, shift);
+            w0 = w1;
+            w1 = __ldg(wp);
+            ++wp;
+            row(__byte_perm(word, 0, 0x4440));
+            row(__byte_perm(word, 0, 0x4441));
+            row(__byte_perm(word, 0, 0x4442));
+            row(__byte_perm(word, 0, 0x4443));
+        }
+        uint32_t word = __funnelshift_r(w0, w1, shift);
+#pragma unroll 1
+        for (uint32_t r = len & 3u; r > 0; --r) {
+            row(word & 0xffu);
+            word >>= 8;
+        }
+        if (lane == 0) p.scores[idx] = (CJ_SAME ? J : C) + move; // MSV_HMM.cpp:112
+    }
+
+    if constexpr (KT > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_slot), "n"(TMEM_COLUMNS) : "memory");
+    }
+}
+
 // ---- database preparation kernels -------------------------------------------------------------------------------
 // Validate residue codes (reference: unordered_map::at throws on a foreign letter, MSV_HMM.cpp:101) -- 16 B per thread.
 __global__ void db_validate_kernel(const uint4* __restrict__ words, uint64_t n_words16, uint64_t n_bytes,

@@ -73,15 +73,16 @@ int msv_host_partition_by_cells(const uint64_t* offsets, size_t n, int parts, si
  *                     exactly the layout of MSV_HMM::emission_scores (MSV_HMM.hpp:27-28, MSV_HMM.cpp:43)
  *   model_length    : LENG + 1 (reference Profile_HMM.cpp:70)
  * The table is re-laid out for the kernel ([residue][column-quad][lane][4], -inf padded) and kept in HBM; each
- * CTA stages it into shared memory with one bulk-async (TMA) copy.
+ * CTA stages it into shared memory with bulk-async (TMA) copies and, for whole-warp geometries, partly into tensor memory.
  * ------------------------------------------------------------------------------------------------------------- */
 int msv_cuda_model_create(const float* emission_scores, size_t model_length, float tr_B_Mk, float tr_E_C, float tr_E_J,
                           int device, msv_model** out);
 int msv_cuda_model_destroy(msv_model* model);
-/* kernel geometry chosen for this model: lanes per sequence (8/16/32), columns per lane, threads per CTA,
- * dynamic shared memory bytes.  Any pointer may be NULL. */
-int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane, int* threads_per_cta,
-                            size_t* shared_bytes);
+/* kernel geometry chosen for this model: lanes per sequence (8/16/32), model columns per lane, how many of those
+ * columns are served from tensor memory (TMEM; -1 = kernel family without TMEM), threads per CTA, dynamic shared
+ * memory bytes.  Any pointer may be NULL. */
+int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane,
+                            int* tensor_columns_per_lane, int* threads_per_cta, size_t* shared_bytes);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Database (device resident).  Uploads residues + offsets, validates the codes, computes the per-length

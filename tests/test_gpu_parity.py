@@ -98,20 +98,42 @@ def test_homologous_sequences_exercise_the_J_state(oracle):
 
 
 @pytest.mark.parametrize("geometry", ["8,4", "8,16", "8,64", "16,8", "16,32", "16,88", "32,4", "32,20", "32,24", "32,44",
-                                       "32,56", "32,60", "32,88"])
+                                       "32,56", "32,60", "32,88",
+                                       # warp kernels: shared memory + KT tensor-memory columns per lane
+                                       "32,4,0", "32,8,0", "32,8,8", "32,20,8", "32,24,16", "32,28,16", "32,44,0", "32,44,8",
+                                       "32,44,16", "32,44,24", "32,44,16,640", "32,64,16", "32,76,16", "32,88,16"])
 def test_every_kernel_geometry(oracle, geometry, monkeypatch):
-    """Lanes-per-sequence x columns-per-lane variants, forced through MSV_CUDA_GEOMETRY, all give reference bits."""
-    G, K = (int(v) for v in geometry.split(","))
-    fits = [n for n in model_files() if int(n.split(".")[0]) <= G * K]
-    name = fits[-1] if fits else None
-    if name is None:
+    """Lanes-per-sequence x columns-per-lane (x tensor-memory columns) variants, forced through MSV_CUDA_GEOMETRY, all
+    give reference bits."""
+    parts = [int(v) for v in geometry.split(",")]
+    G, K = parts[0], parts[1]
+    KT = parts[2] if len(parts) > 2 else -1
+    limit = G * K - (1 if KT >= 0 else 0)  # the warp kernel needs one padding column
+    fits = [n for n in model_files() if int(n.split(".")[0]) <= limit]
+    if not fits:
         pytest.skip("no fixture model fits this geometry")
+    name = fits[-1]
     monkeypatch.setenv("MSV_CUDA_GEOMETRY", geometry)
     model, table, tr3 = device_model(oracle, name)
-    assert model.geometry["lanes_per_sequence"] == G and model.geometry["columns_per_lane"] == K
+    geo = model.geometry
+    assert (geo["lanes_per_sequence"], geo["columns_per_lane"], geo["tensor_columns_per_lane"]) == (G, K, KT)
     rng = np.random.default_rng(G * 1000 + K)
     n = max(64, min(4000, int(4e7 / (int(name.split(".")[0]) * 150))))
     seqs, codes, offsets = random_db(rng, n, 0, 300)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+
+
+def test_general_E_transitions_keep_C_and_J_apart(oracle):
+    """tr_E_C != tr_E_J selects the kernel variant that carries C separately (the reference always has them equal)."""
+    h = oracle.load_hmm(hmm_path("1400.hmm"))
+    table, tr3 = oracle.prepare(h["match_emissions"])
+    tr3 = tr3.copy()
+    tr3[1] = np.float32(-1.25)  # E -> C
+    tr3[2] = np.float32(-0.40)  # E -> J
+    model = msv.Model(table, tr3[0], tr3[1], tr3[2])
+    rng = np.random.default_rng(9)
+    seqs, codes, offsets = random_db(rng, 600, 0, 300)
     want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
     assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
 
