@@ -190,7 +190,7 @@ def main() -> None:
     import torch.distributed as dist
 
     import hmm_fasta_viterbi_b200 as msv
-    from hmm_fasta_viterbi_b200 import _cabi
+    from hmm_fasta_viterbi_b200 import _cabi, sharded
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,11 +212,7 @@ def main() -> None:
         codes, offsets = packed.residues, packed.offsets
     else:
         packed = msv.Packed_sequences.synthetic_swissprot_like(args.sequences, SEED)
-        bounds = _cabi.partition_by_cells(packed.offsets, world)
-        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-        base = int(packed.offsets[lo])
-        codes = packed.residues[base:int(packed.offsets[hi])]
-        offsets = (packed.offsets[lo:hi + 1] - np.uint64(base)).astype(np.uint64)
+        codes, offsets, _, _ = sharded.local_slice(packed.residues, packed.offsets, rank, world)
     n_local = len(offsets) - 1
     cells_local = leng * float(offsets[-1])
 
