@@ -133,6 +133,7 @@ struct Device_guard {
 } // namespace
 
 // ---- opaque handles ---------------------------------------------------------------------------------------------
+constexpr int kMaxChunks = 32; // pipelined upload: at most this many upload/scan stages per batch
 struct msv_db {
     int device = 0;
     size_t n = 0;
@@ -151,6 +152,10 @@ struct msv_db {
     unsigned int* d_queue = nullptr;
     unsigned long long* d_first_bad = nullptr;
     std::vector<float2> h_length_tr; // host copy, extended lazily
+    // pipelined upload (msv_cuda_score_batch): copy engine and scan overlap
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaEvent_t stage_copied[kMaxChunks] = {};
+    cudaEvent_t reserved = nullptr;
 };
 
 struct msv_model {
@@ -180,13 +185,18 @@ int db_release(msv_db* db) {
     cudaFree(db->d_hist);
     cudaFree(db->d_queue);
     cudaFree(db->d_first_bad);
+    if (db->copy_stream) {
+        cudaStreamDestroy(db->copy_stream);
+        cudaStreamDestroy(db->compute_stream);
+        for (auto ev : db->stage_copied) cudaEventDestroy(ev);
+        cudaEventDestroy(db->reserved);
+    }
     delete db;
     return MSV_OK;
 }
 
-// (Re)fill `db` from host buffers: upload, validate, per-length transitions, longest-first order.  Work is queued on
-// `stream`; the function returns after the validation result has been read back (one small synchronisation).
-int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n, cudaStream_t stream) {
+// Host pass over the offsets: monotonic, total and longest sequence.
+int db_check_offsets(const uint8_t* residues, const uint64_t* offsets, size_t n, uint64_t* total_out, uint64_t* longest_out) {
     if (n > 0 && (!offsets || offsets[0] != 0)) return fail(MSV_ERR_INVALID_ARGUMENT, "offsets[0] must be 0");
     if (n >= (1ull << 32) - 1) return fail(MSV_ERR_INVALID_ARGUMENT, "more than 2^32-2 sequences in one database");
     uint64_t longest = 0;
@@ -197,8 +207,13 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
     const uint64_t total = n ? offsets[n] : 0;
     if (total > 0 && !residues) return fail(MSV_ERR_INVALID_ARGUMENT, "residues is NULL");
     if (longest >= (1ull << 31)) return fail(MSV_ERR_INVALID_ARGUMENT, "sequence longer than 2^31-1 residues");
+    *total_out = total;
+    *longest_out = longest;
+    return MSV_OK;
+}
 
-    // ---- capacities ----
+// Grow-only device buffers + the per-length (tr_loop, tr_move) table (host libm, reference MSV_HMM.cpp:59-64).
+int db_reserve(msv_db* db, uint64_t total, size_t n, uint64_t longest, cudaStream_t stream) {
     const size_t need_res = static_cast<size_t>(total) + msv::kResiduePadBytes + 16;
     if (need_res > db->cap_residues) {
         cudaFree(db->d_residues);
@@ -224,11 +239,9 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
     }
     if (!db->d_hist) {
         MSV_CUDA_TRY(cudaMalloc(&db->d_hist, 2 * kBuckets * sizeof(uint32_t)));
-        MSV_CUDA_TRY(cudaMalloc(&db->d_queue, sizeof(unsigned int)));
+        MSV_CUDA_TRY(cudaMalloc(&db->d_queue, kMaxChunks * sizeof(unsigned int)));
         MSV_CUDA_TRY(cudaMalloc(&db->d_first_bad, sizeof(unsigned long long)));
     }
-
-    // ---- per-length loop/move scores, host libm (reference MSV_HMM.cpp:59-64) ----
     if (db->h_length_tr.size() < longest + 1) {
         const size_t from = db->h_length_tr.size();
         db->h_length_tr.resize(longest + 1);
@@ -238,8 +251,7 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
             db->h_length_tr[L] = make_float2(lo, mv);
         }
     }
-    const bool tr_grew = db->h_length_tr.size() > db->cap_tr;
-    if (tr_grew) {
+    if (db->h_length_tr.size() > db->cap_tr) {
         cudaFree(db->d_length_tr);
         db->d_length_tr = nullptr;
         db->cap_tr = 0;
@@ -248,48 +260,46 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
                                      cudaMemcpyHostToDevice, stream));
         db->cap_tr = db->h_length_tr.size();
     }
-
-    // ---- upload ----
-    if (total) MSV_CUDA_TRY(cudaMemcpyAsync(db->d_residues, residues, total, cudaMemcpyHostToDevice, stream));
-    MSV_CUDA_TRY(cudaMemsetAsync(db->d_residues + total, 0, msv::kResiduePadBytes + 16, stream));
-    if (n) {
-        MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-    } else {
-        MSV_CUDA_TRY(cudaMemsetAsync(db->d_offsets, 0, sizeof(uint64_t), stream));
-    }
-
-    db->n = n;
-    db->total = total;
-    db->longest = longest;
-    if (n == 0) return MSV_OK;
-
-    // ---- validate codes + bucket longest-first on the device ----
     const unsigned long long none = ~0ull;
     MSV_CUDA_TRY(cudaMemcpyAsync(db->d_first_bad, &none, sizeof none, cudaMemcpyHostToDevice, stream));
-    if (total) {
-        const uint64_t words = (total + 15) / 16;
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, kMaxChunks * sizeof(unsigned int), stream));
+    return MSV_OK;
+}
+
+// Validate the residue codes of sequences [first, first+count) and bucket them longest-first into
+// d_order[first .. first+count) (indices relative to `first`).  Everything is queued on `stream`.
+int db_prepare_range(msv_db* db, size_t first, size_t count, uint64_t residue_begin, uint64_t residue_end, uint64_t longest,
+                     cudaStream_t stream) {
+    if (count == 0) return MSV_OK;
+    if (residue_end > residue_begin) {
+        // 16-byte words that cover the range; neighbouring ranges may be checked twice, which is harmless
+        const uint64_t word_begin = residue_begin / 16, word_end = (residue_end + 15) / 16;
+        const uint64_t words = word_end - word_begin;
         const int blocks = static_cast<int>(std::min<uint64_t>((words + 255) / 256, 148 * 16));
-        msv::db_validate_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(db->d_residues), words, total,
-                                                             db->d_first_bad);
+        msv::db_validate_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(db->d_residues) + word_begin, words,
+                                                             residue_end - word_begin * 16, word_begin * 16, db->d_first_bad);
         ++g_launches;
     }
     uint32_t shift = 0;
     while ((longest >> shift) >= kBuckets) ++shift;
-    MSV_CUDA_TRY(cudaMemsetAsync(db->d_hist, 0, 2 * kBuckets * sizeof(uint32_t), stream));
-    const uint32_t n32 = static_cast<uint32_t>(n);
     const uint32_t used_buckets = static_cast<uint32_t>(std::min<uint64_t>((longest >> shift) + 1, kBuckets));
-    const int blocks_n = static_cast<int>((n + 255) / 256);
-    msv::db_histogram_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets, n32, shift, used_buckets, db->d_hist);
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_hist, 0, used_buckets * sizeof(uint32_t), stream));
+    const uint32_t n32 = static_cast<uint32_t>(count);
+    const int blocks_n = static_cast<int>((count + 255) / 256);
+    msv::db_histogram_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets + first, n32, shift, used_buckets, db->d_hist);
     msv::db_scan_kernel<<<1, 1024, 0, stream>>>(db->d_hist, used_buckets, db->d_hist + kBuckets);
-    msv::db_scatter_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets, n32, shift, used_buckets, db->d_hist + kBuckets,
-                                                         db->d_order);
+    msv::db_scatter_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets + first, n32, shift, used_buckets, db->d_hist + kBuckets,
+                                                         db->d_order + first);
     g_launches += 3;
     MSV_CUDA_TRY(cudaGetLastError());
+    return MSV_OK;
+}
 
-    unsigned long long first_bad = none;
+int db_read_validation(msv_db* db, const uint8_t* residues, cudaStream_t stream) {
+    unsigned long long first_bad = ~0ull;
     MSV_CUDA_TRY(cudaMemcpyAsync(&first_bad, db->d_first_bad, sizeof first_bad, cudaMemcpyDeviceToHost, stream));
     MSV_CUDA_TRY(cudaStreamSynchronize(stream));
-    if (first_bad != none) {
+    if (first_bad != ~0ull) {
         db->n = 0;
         return fail(MSV_ERR_BAD_RESIDUE, "residue code %u at position %llu is outside 0..19",
                     static_cast<unsigned>(residues[first_bad]), first_bad);
@@ -297,30 +307,52 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
     return MSV_OK;
 }
 
-int launch_scan(msv_model* model, msv_db* db, float* d_scores, cudaStream_t stream) {
-    if (db->n == 0) return MSV_OK;
+// (Re)fill `db` from host buffers in one piece: upload, validate, per-length transitions, longest-first order.
+// Returns after the validation result has been read back (one small synchronisation).
+int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n, cudaStream_t stream) {
+    uint64_t total = 0, longest = 0;
+    if (int rc = db_check_offsets(residues, offsets, n, &total, &longest)) return rc;
+    if (int rc = db_reserve(db, total, n, longest, stream)) return rc;
+    if (total) MSV_CUDA_TRY(cudaMemcpyAsync(db->d_residues, residues, total, cudaMemcpyHostToDevice, stream));
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_residues + total, 0, msv::kResiduePadBytes + 16, stream));
+    if (n) {
+        MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    } else {
+        MSV_CUDA_TRY(cudaMemsetAsync(db->d_offsets, 0, sizeof(uint64_t), stream));
+    }
+    db->n = n;
+    db->total = total;
+    db->longest = longest;
+    if (n == 0) return MSV_OK;
+    if (int rc = db_prepare_range(db, 0, n, 0, total, longest, stream)) return rc;
+    return db_read_validation(db, residues, stream);
+}
+
+// One launch of the scan over sequences [first, first+count) of `db`; scores go to d_scores[first ..).
+int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, int queue_slot, float* d_scores, cudaStream_t stream) {
+    if (count == 0) return MSV_OK;
     const Geometry* geo = model->geo;
     msv::Scan_params p{};
     p.table = model->d_table;
     p.residues = db->d_residues;
-    p.offsets = db->d_offsets;
-    p.order = db->d_order;
+    p.offsets = db->d_offsets + first;
+    p.order = db->d_order + first;
     p.length_tr = db->d_length_tr;
-    p.scores = d_scores;
-    p.queue_head = db->d_queue;
-    p.n = static_cast<uint32_t>(db->n);
+    p.scores = d_scores + first;
+    p.queue_head = db->d_queue + queue_slot;
+    p.n = static_cast<uint32_t>(count);
     p.table_bytes = static_cast<uint32_t>(model->shared_bytes);
     p.tr_by_sequence = 0;
     p.tr_B_Mk = model->tr_B_Mk;
     p.tr_E_C = model->tr_E_C;
     p.tr_E_J = model->tr_E_J;
-    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, sizeof(unsigned int), stream));
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue + queue_slot, 0, sizeof(unsigned int), stream));
     // persistent CTAs: one per SM, but never more groups than sequences
     const size_t groups_per_cta = static_cast<size_t>(geo->threads / geo->G);
-    const int ctas = static_cast<int>(std::max<size_t>(1, std::min<size_t>(model->sm_count, (db->n + groups_per_cta - 1) / groups_per_cta)));
+    const int ctas = static_cast<int>(std::max<size_t>(1, std::min<size_t>(model->sm_count, (count + groups_per_cta - 1) / groups_per_cta)));
     int threads = geo->threads;
     if (ctas == 1) { // latency path: do not launch warps that would find the queue empty
-        const size_t warps = (db->n * geo->G + 31) / 32;
+        const size_t warps = (count * geo->G + 31) / 32;
         threads = static_cast<int>(std::min<size_t>(geo->threads, std::max<size_t>(1, warps) * 32));
     }
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
@@ -328,6 +360,48 @@ int launch_scan(msv_model* model, msv_db* db, float* d_scores, cudaStream_t stre
     ++g_launches;
     MSV_CUDA_TRY(cudaGetLastError());
     return MSV_OK;
+}
+
+// End-to-end batch with the upload hidden behind the scan: the database is cut into contiguous stages of sequences;
+// stage s+1 is copied to the device (copy stream) while stage s is validated, bucketed and scanned (compute stream).
+int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n,
+                          float* scores_host) {
+    uint64_t total = 0, longest = 0;
+    if (int rc = db_check_offsets(residues, offsets, n, &total, &longest)) return rc;
+    if (!db->copy_stream) {
+        MSV_CUDA_TRY(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
+        MSV_CUDA_TRY(cudaStreamCreateWithFlags(&db->compute_stream, cudaStreamNonBlocking));
+        for (auto& ev : db->stage_copied) MSV_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        MSV_CUDA_TRY(cudaEventCreateWithFlags(&db->reserved, cudaEventDisableTiming));
+    }
+    cudaStream_t copy = db->copy_stream, compute = db->compute_stream;
+    if (int rc = db_reserve(db, total, n, longest, compute)) return rc;
+    MSV_CUDA_TRY(cudaEventRecord(db->reserved, compute));
+    MSV_CUDA_TRY(cudaStreamWaitEvent(copy, db->reserved, 0)); // buffers may have been reallocated
+    db->n = n;
+    db->total = total;
+    db->longest = longest;
+    if (n == 0) return MSV_OK;
+
+    // stages of roughly equal residue count; small batches are not split
+    const uint64_t min_stage_bytes = 4ull << 20;
+    const int stages = static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>(kMaxChunks, total / min_stage_bytes)));
+    size_t bounds[kMaxChunks + 1];
+    if (int rc = msv_host_partition_by_cells(offsets, n, stages, bounds)) return rc;
+
+    MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy));
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_residues + total, 0, msv::kResiduePadBytes + 16, copy));
+    for (int s = 0; s < stages; ++s) {
+        const size_t first = bounds[s], last = bounds[s + 1];
+        const uint64_t begin = offsets[first], end = offsets[last];
+        if (end > begin) MSV_CUDA_TRY(cudaMemcpyAsync(db->d_residues + begin, residues + begin, end - begin, cudaMemcpyHostToDevice, copy));
+        MSV_CUDA_TRY(cudaEventRecord(db->stage_copied[s], copy));
+        MSV_CUDA_TRY(cudaStreamWaitEvent(compute, db->stage_copied[s], 0));
+        if (int rc = db_prepare_range(db, first, last - first, begin, end, longest, compute)) return rc;
+        if (int rc = launch_scan(model, db, first, last - first, s, db->d_scores, compute)) return rc;
+    }
+    MSV_CUDA_TRY(cudaMemcpyAsync(scores_host, db->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, compute));
+    return db_read_validation(db, residues, compute);
 }
 
 } // namespace
@@ -571,7 +645,7 @@ int msv_cuda_db_score_device(msv_model* model, msv_db* db, float* scores_device,
     if (db->n && !scores_device) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_device is NULL");
     Device_guard guard(model->device);
     MSV_CUDA_TRY(guard.status);
-    return launch_scan(model, db, scores_device, static_cast<cudaStream_t>(cuda_stream));
+    return launch_scan(model, db, 0, db->n, 0, scores_device, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host) {
@@ -580,7 +654,7 @@ int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host) {
     if (db->n && !scores_host) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_host is NULL");
     Device_guard guard(model->device);
     MSV_CUDA_TRY(guard.status);
-    if (int rc = launch_scan(model, db, db->d_scores, nullptr)) return rc;
+    if (int rc = launch_scan(model, db, 0, db->n, 0, db->d_scores, nullptr)) return rc;
     if (db->n) MSV_CUDA_TRY(cudaMemcpy(scores_host, db->d_scores, db->n * sizeof(float), cudaMemcpyDeviceToHost));
     return MSV_OK;
 }
@@ -595,11 +669,7 @@ int msv_cuda_score_batch(msv_model* model, const uint8_t* residues, const uint64
         if (!model->workspace) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
         model->workspace->device = model->device;
     }
-    msv_db* db = model->workspace;
-    if (int rc = db_fill(db, residues, offsets, n, nullptr)) return rc;
-    if (int rc = launch_scan(model, db, db->d_scores, nullptr)) return rc;
-    if (n) MSV_CUDA_TRY(cudaMemcpy(scores_host, db->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost));
-    return MSV_OK;
+    return score_batch_pipelined(model, model->workspace, residues, offsets, n, scores_host);
 }
 
 int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score) {

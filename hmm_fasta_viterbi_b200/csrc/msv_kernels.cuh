@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
 
 // ---- database preparation kernels -------------------------------------------------------------------------------
 // Validate residue codes (reference: unordered_map::at throws on a foreign letter, MSV_HMM.cpp:101) -- 16 B per thread.
-__global__ void db_validate_kernel(const uint4* __restrict__ words, uint64_t n_words16, uint64_t n_bytes,
+__global__ void db_validate_kernel(const uint4* __restrict__ words, uint64_t n_words16, uint64_t n_bytes, uint64_t base_position,
                                    unsigned long long* __restrict__ first_bad) {
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_words16; i += stride) {
@@ -467,7 +467,8 @@ __global__ void db_validate_kernel(const uint4* __restrict__ words, uint64_t n_w
             if (t & 0x80808080u) {
                 for (int b = 0; b < 4; ++b) {
                     const uint64_t pos = i * 16 + k * 4 + b;
-                    if (pos < n_bytes && ((v[k] >> (8 * b)) & 0xffu) >= kAlphabet) atomicMin(first_bad, static_cast<unsigned long long>(pos));
+                    if (pos < n_bytes && ((v[k] >> (8 * b)) & 0xffu) >= kAlphabet)
+                        atomicMin(first_bad, static_cast<unsigned long long>(base_position + pos));
                 }
             }
         }
