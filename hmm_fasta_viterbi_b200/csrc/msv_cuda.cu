@@ -340,6 +340,7 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, int qu
     p.length_tr = db->d_length_tr;
     p.scores = d_scores + first;
     p.queue_head = db->d_queue + queue_slot;
+    p.first_bad = db->d_first_bad;
     p.n = static_cast<uint32_t>(count);
     p.table_bytes = static_cast<uint32_t>(model->shared_bytes);
     p.tr_by_sequence = 0;

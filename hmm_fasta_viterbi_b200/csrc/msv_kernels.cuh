@@ -41,6 +41,7 @@ struct Scan_params {
     const float2* length_tr;  // (tr_loop, tr_move): indexed by length, or by sequence when tr_by_sequence != 0
     float* scores;            // n, original order
     unsigned int* queue_head; // work queue cursor, zero before launch
+    const unsigned long long* first_bad; // position of the first invalid residue code found by db_validate_kernel, or ~0
     uint32_t n;
     uint32_t table_bytes;
     uint32_t tr_by_sequence;
@@ -105,6 +106,9 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t table_ready;
+
+    // never index the table with an unvalidated residue code: the validation kernel precedes this launch on the stream
+    if (p.first_bad != nullptr && *p.first_bad != ~0ull) return;
 
     // ---- stage the emission table: one thread programs the TMA unit, everybody waits on the mbarrier ----
     if (threadIdx.x == 0) mbarrier_init(&table_ready, 1);
@@ -312,6 +316,9 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+
+    // never index the table with an unvalidated residue code: the validation kernel precedes this launch on the stream
+    if (p.first_bad != nullptr && *p.first_bad != ~0ull) return;
 
     // ---- stage the shared-memory part with the TMA unit ----
     if (threadIdx.x == 0) mbarrier_init(&table_ready, 1);
