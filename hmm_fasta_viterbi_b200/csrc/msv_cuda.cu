@@ -69,6 +69,11 @@ template <int K, int KT> constexpr Geometry warp_entry() {
                     msv::msv_scan_warp_kernel<K, KT, warp_threads_for(K, KT), true>};
 }
 
+constexpr int quad_threads_for(int K) { return K <= 12 ? 1024 : K <= 28 ? 768 : 512; }
+template <int K, int KT> constexpr Geometry quad_entry() { // four warps (128 lanes) per sequence
+    return Geometry{128, K, KT, quad_threads_for(K), msv::msv_scan_quad_kernel<K, KT, quad_threads_for(K), false>,
+                    msv::msv_scan_quad_kernel<K, KT, quad_threads_for(K), true>};
+}
 template <int K, int KT, int T> constexpr Geometry warp_entry_threads() {
     return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false>, msv::msv_scan_warp_kernel<K, KT, T, true>};
 }
@@ -81,11 +86,18 @@ template <int K, int KT, int T> constexpr Geometry warp_entry_threads() {
     X(A, 76) X(A, 80) X(A, 84) X(A, 88)
 #define MSV_GENERIC(G, K) generic_entry<G, K>(),
 #define MSV_WARP(KT, K) warp_entry<K, KT>(),
+#define MSV_FOR_EACH_K_FROM_28(X, A)                                                                                   \
+    X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) X(A, 76)  \
+    X(A, 80) X(A, 84) X(A, 88)
 const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(MSV_GENERIC, 16) MSV_FOR_EACH_K(MSV_GENERIC, 32)
                                      MSV_WARP(0, 4) MSV_WARP(0, 8) MSV_WARP(8, 8) MSV_WARP(8, 12) MSV_WARP(8, 16) MSV_WARP(8, 20)
-                                         MSV_FOR_EACH_K_FROM_24(MSV_WARP, 16) MSV_WARP(0, 44) MSV_WARP(8, 44) MSV_WARP(24, 44)
-                                             warp_entry_threads<44, 16, 640>(), warp_entry_threads<44, 16, 448>(),
-                                 warp_entry_threads<44, 16, 384>()};
+                                         MSV_WARP(16, 16) MSV_WARP(16, 20) MSV_WARP(24, 24) MSV_FOR_EACH_K_FROM_24(MSV_WARP, 16)
+                                             MSV_FOR_EACH_K_FROM_28(MSV_WARP, 24) MSV_WARP(0, 44) MSV_WARP(8, 44)
+                                                 warp_entry_threads<44, 16, 640>(), warp_entry_threads<44, 16, 448>(),
+                                 warp_entry_threads<44, 16, 384>(),
+                                 quad_entry<4, 0>(), quad_entry<8, 8>(), quad_entry<12, 8>(), quad_entry<16, 16>(), quad_entry<20, 16>(),
+                                 quad_entry<24, 16>(), quad_entry<28, 16>(), quad_entry<32, 16>(), quad_entry<36, 16>(),
+                                 quad_entry<40, 24>(), quad_entry<44, 24>()};
 
 const Geometry* find_geometry(int G, int K, int KT, int threads = 0) {
     for (const auto& g : g_geometries)
@@ -95,10 +107,10 @@ const Geometry* find_geometry(int G, int K, int KT, int threads = 0) {
 
 int round_up4(size_t v) { return static_cast<int>((v + 3) / 4 * 4); }
 
-// Fewer lanes per sequence amortise the per-row bookkeeping over more cells, as long as the row still fits a lane's
-// registers.  Models that need a whole warp per sequence use the shared-memory + tensor-memory split; that kernel
-// needs the last column of lane 31 to be padding, hence 32*K > columns there.
-// MSV_CUDA_GEOMETRY="G,K[,KT]" overrides the choice (tuning aid; without KT the generic kernel is selected).
+// Default: one warp per sequence with the shared-memory + tensor-memory split (that kernel needs the last column of
+// lane 31 to be padding, hence 32*K > columns).  The generic family (8/16/32 lanes per sequence, shared memory only) is
+// kept for comparison and for devices/contexts where TMEM is unavailable.
+// MSV_CUDA_GEOMETRY="G,K[,KT[,threads]]" overrides the choice (tuning aid; without KT the generic kernel is selected).
 const Geometry* choose_geometry(size_t columns) {
     if (const char* env = std::getenv("MSV_CUDA_GEOMETRY")) {
         int G = 0, K = 0, KT = -1, T = 0;
@@ -108,14 +120,21 @@ const Geometry* choose_geometry(size_t columns) {
         if (got >= 3 && static_cast<size_t>(G) * K > columns)
             if (const Geometry* g = find_geometry(G, K, KT, T)) return g;
     }
-    constexpr int preferred_K = 64;
-    for (int G : {8, 16}) {
-        const int K = std::max(4, round_up4((columns + G - 1) / G));
-        if (K <= preferred_K) return find_geometry(G, K, -1);
-    }
-    const int K = std::max(4, round_up4((columns + 1 + 31) / 32)); // 32*K > columns
+    // Measured on B200 over the 24 fixture models (profiles/r01/sweep_models_v2.jsonl, sweep_kt_v2.jsonl): the
+    // warp-per-sequence kernel with the shared-memory/tensor-memory split wins at every model length, with 16 tensor-memory
+    // columns per lane (24 for the longest rows, 8 or none for the shortest).
+    const int K = std::max(4, round_up4((columns + 1 + 31) / 32)); // 32*K > columns: lane 31 ends in a padding column
     if (K > msv::kMaxColumnsPerLane) return nullptr;
-    return find_geometry(32, K, K >= 24 ? 16 : K >= 12 ? 8 : 0);
+    const int KT = K >= 72 ? 24 : K >= 16 ? 16 : K >= 8 ? 8 : 0;
+    return find_geometry(32, K, KT);
+}
+
+// Four warps per sequence: the plan for few/long sequences and for models beyond one warp's registers.
+const Geometry* choose_quad_geometry(size_t columns) {
+    const int K = std::max(4, round_up4((columns + 127) / 128));
+    for (const auto& g : g_geometries)
+        if (g.G == 128 && g.K == K) return &g;
+    return nullptr;
 }
 
 struct Device_guard {
@@ -161,10 +180,16 @@ struct msv_db {
 struct msv_model {
     int device = 0;
     size_t model_length = 0;
-    const Geometry* geo = nullptr;
-    size_t table_bytes = 0;  // whole table in HBM (shared-memory part followed by tensor-memory part)
-    size_t shared_bytes = 0; // dynamic shared memory of the scan kernel
-    float4* d_table = nullptr;
+    // A plan = one kernel geometry + the emission table laid out for it (shared-memory part, then tensor-memory part).
+    struct Plan {
+        const Geometry* geo = nullptr;
+        size_t table_bytes = 0;  // whole table in HBM
+        size_t shared_bytes = 0; // dynamic shared memory of the scan kernel
+        float4* d_table = nullptr;
+    };
+    Plan bulk;  // many sequences: one warp (or a lane group) per sequence
+    Plan quad;  // few or very long sequences, single-sequence calls: four warps per sequence (may be absent)
+    bool forced = false; // MSV_CUDA_GEOMETRY was given: always use `bulk`
     float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
     int sm_count = 0;
     msv_db* workspace = nullptr; // reused by msv_cuda_score_batch / msv_cuda_score_sequence
@@ -328,12 +353,22 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
     return db_read_validation(db, residues, stream);
 }
 
+// Which plan scans `count` sequences: the four-warp plan when there are too few sequences to fill the warp slots of the
+// bulk plan (the makespan would be one long sequence on a sixteenth of an SM), or when the model has no bulk plan.
+const msv_model::Plan& pick_plan(const msv_model* model, size_t count) {
+    if (!model->bulk.geo) return model->quad;
+    if (model->forced || !model->quad.geo) return model->bulk;
+    const size_t bulk_slots = static_cast<size_t>(model->sm_count) * (model->bulk.geo->threads / model->bulk.geo->G);
+    return count < 2 * bulk_slots ? model->quad : model->bulk;
+}
+
 // One launch of the scan over sequences [first, first+count) of `db`; scores go to d_scores[first ..).
 int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, int queue_slot, float* d_scores, cudaStream_t stream) {
     if (count == 0) return MSV_OK;
-    const Geometry* geo = model->geo;
+    const msv_model::Plan& plan = pick_plan(model, count);
+    const Geometry* geo = plan.geo;
     msv::Scan_params p{};
-    p.table = model->d_table;
+    p.table = plan.d_table;
     p.residues = db->d_residues;
     p.offsets = db->d_offsets + first;
     p.order = db->d_order + first;
@@ -342,22 +377,26 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, int qu
     p.queue_head = db->d_queue + queue_slot;
     p.first_bad = db->d_first_bad;
     p.n = static_cast<uint32_t>(count);
-    p.table_bytes = static_cast<uint32_t>(model->shared_bytes);
+    p.table_bytes = static_cast<uint32_t>(plan.shared_bytes);
     p.tr_by_sequence = 0;
     p.tr_B_Mk = model->tr_B_Mk;
     p.tr_E_C = model->tr_E_C;
     p.tr_E_J = model->tr_E_J;
     MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue + queue_slot, 0, sizeof(unsigned int), stream));
-    // persistent CTAs: one per SM, but never more groups than sequences
-    const size_t groups_per_cta = static_cast<size_t>(geo->threads / geo->G);
-    const int ctas = static_cast<int>(std::max<size_t>(1, std::min<size_t>(model->sm_count, (count + groups_per_cta - 1) / groups_per_cta)));
-    int threads = geo->threads;
-    if (ctas == 1) { // latency path: do not launch warps that would find the queue empty
-        const size_t warps = (count * geo->G + 31) / 32;
-        threads = static_cast<int>(std::min<size_t>(geo->threads, std::max<size_t>(1, warps) * 32));
+    // persistent CTAs, at most one per SM; a "slot" scans one sequence at a time (lane group, warp or four warps)
+    const size_t threads_per_slot = static_cast<size_t>(geo->G);
+    const size_t slots_per_cta = geo->threads / threads_per_slot;
+    size_t ctas, slots;
+    if (geo->G == 128) { // spread few sequences over as many SMs as possible
+        ctas = std::min<size_t>(model->sm_count, count);
+        slots = std::min<size_t>(slots_per_cta, (count + ctas - 1) / ctas);
+    } else {
+        ctas = std::max<size_t>(1, std::min<size_t>(model->sm_count, (count + slots_per_cta - 1) / slots_per_cta));
+        slots = ctas == 1 ? std::min<size_t>(slots_per_cta, count) : slots_per_cta;
     }
+    const int threads = static_cast<int>(std::max<size_t>(32, (slots * threads_per_slot + 31) / 32 * 32));
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
-    (cj_same ? geo->fn_cj_same : geo->fn)<<<ctas, threads, model->shared_bytes, stream>>>(p);
+    (cj_same ? geo->fn_cj_same : geo->fn)<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
     ++g_launches;
     MSV_CUDA_TRY(cudaGetLastError());
     return MSV_OK;
@@ -520,10 +559,11 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
     if (device < 0 || device >= count) return fail(MSV_ERR_INVALID_ARGUMENT, "device %d out of range (have %d)", device, count);
 
     const size_t columns = model_length - 1; // without the dummy M0
-    const Geometry* geo = choose_geometry(columns);
-    if (!geo)
-        return fail(MSV_ERR_MODEL_TOO_LONG, "model of %zu columns exceeds %d lanes x %d columns", columns, 32,
-                    msv::kMaxColumnsPerLane);
+    const bool forced = std::getenv("MSV_CUDA_GEOMETRY") != nullptr;
+    const Geometry* bulk_geo = choose_geometry(columns);
+    const Geometry* quad_geo = choose_quad_geometry(columns);
+    if (!bulk_geo && !quad_geo)
+        return fail(MSV_ERR_MODEL_TOO_LONG, "model of %zu columns exceeds the on-chip table capacity (128 lanes x 44 columns)", columns);
 
     Device_guard guard(device);
     MSV_CUDA_TRY(guard.status);
@@ -533,53 +573,61 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         return fail(MSV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major,
                     prop.minor);
 
-    // kernel layout (see msv_kernels.cuh).  Lane g owns model columns g*K + j + 1, j = 0..K-1; -inf beyond the model.
-    //   shared-memory part : [residue][quad q][lane g][4]   j = KT + 4q + c      (generic kernel: KT = 0)
-    //   tensor-memory part : [residue][lane g][KT]          j = 0 .. KT-1        (warp kernel with KT > 0 only)
-    const int G = geo->G, K = geo->K, KT = std::max(geo->KT, 0), KS = K - KT;
-    const size_t shared_floats = static_cast<size_t>(MSV_ALPHABET) * KS * G;
-    const size_t floats = shared_floats + static_cast<size_t>(MSV_ALPHABET) * KT * G;
-    std::vector<float> laid(std::max<size_t>(floats, 4), -std::numeric_limits<float>::infinity());
-    const auto emission = [&](int res, int g, int j) {
-        const size_t col = static_cast<size_t>(g) * K + j + 1;
-        return col <= columns ? emission_scores[res * model_length + col] : -std::numeric_limits<float>::infinity();
-    };
-    for (int res = 0; res < MSV_ALPHABET; ++res)
-        for (int g = 0; g < G; ++g) {
-            for (int js = 0; js < KS; ++js)
-                laid[((static_cast<size_t>(res) * (KS / 4) + js / 4) * G + g) * 4 + js % 4] = emission(res, g, KT + js);
-            for (int jt = 0; jt < KT; ++jt)
-                laid[shared_floats + (static_cast<size_t>(res) * G + g) * KT + jt] = emission(res, g, jt);
-        }
-
     auto* model = new (std::nothrow) msv_model();
     if (!model) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
     model->device = device;
     model->model_length = model_length;
-    model->geo = geo;
-    model->table_bytes = laid.size() * sizeof(float);
-    model->shared_bytes = geo->shared_bytes();
     model->tr_B_Mk = tr_B_Mk;
     model->tr_E_C = tr_E_C;
     model->tr_E_J = tr_E_J;
     model->sm_count = prop.multiProcessorCount;
-    if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < model->shared_bytes + 64) {
-        const size_t need = model->shared_bytes;
-        delete model;
-        return fail(MSV_ERR_MODEL_TOO_LONG, "emission table of %zu bytes exceeds shared memory", need);
+    model->forced = forced;
+
+    // kernel layout (see msv_kernels.cuh).  Lane g of a sequence's G lanes owns model columns g*K + j + 1, j = 0..K-1;
+    // -inf beyond the model.
+    //   shared-memory part : [residue][quad q][lane g][4]   j = KT + 4q + c      (generic family: KT = 0)
+    //   tensor-memory part : [residue][lane g][KT]          j = 0 .. KT-1
+    const auto build = [&](const Geometry* geo, msv_model::Plan& plan) -> cudaError_t {
+        const int G = geo->G, K = geo->K, KT = std::max(geo->KT, 0), KS = K - KT;
+        const size_t shared_floats = static_cast<size_t>(MSV_ALPHABET) * KS * G;
+        const size_t floats = shared_floats + static_cast<size_t>(MSV_ALPHABET) * KT * G;
+        std::vector<float> laid(std::max<size_t>(floats, 4), -std::numeric_limits<float>::infinity());
+        const auto emission = [&](int res, int g, int j) {
+            const size_t col = static_cast<size_t>(g) * K + j + 1;
+            return col <= columns ? emission_scores[res * model_length + col] : -std::numeric_limits<float>::infinity();
+        };
+        for (int res = 0; res < MSV_ALPHABET; ++res)
+            for (int g = 0; g < G; ++g) {
+                for (int js = 0; js < KS; ++js)
+                    laid[((static_cast<size_t>(res) * (KS / 4) + js / 4) * G + g) * 4 + js % 4] = emission(res, g, KT + js);
+                for (int jt = 0; jt < KT; ++jt)
+                    laid[shared_floats + (static_cast<size_t>(res) * G + g) * KT + jt] = emission(res, g, jt);
+            }
+        plan.table_bytes = laid.size() * sizeof(float);
+        plan.shared_bytes = geo->shared_bytes();
+        if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < plan.shared_bytes + 1024) return cudaErrorInvalidConfiguration;
+        cudaError_t err = cudaMalloc(&plan.d_table, plan.table_bytes);
+        if (err == cudaSuccess) err = cudaMemcpy(plan.d_table, laid.data(), plan.table_bytes, cudaMemcpyHostToDevice);
+        for (Scan_kernel fn : {geo->fn, geo->fn_cj_same})
+            if (err == cudaSuccess)
+                err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(plan.shared_bytes));
+        if (err == cudaSuccess) plan.geo = geo;
+        return err;
+    };
+    cudaError_t err = cudaSuccess;
+    if (bulk_geo) err = build(bulk_geo, model->bulk);
+    if (err == cudaSuccess && quad_geo && !forced) {
+        const cudaError_t quad_err = build(quad_geo, model->quad);
+        if (!bulk_geo) err = quad_err; // the quad plan is optional unless it is the only one
     }
-    cudaError_t err = cudaMalloc(&model->d_table, model->table_bytes);
-    if (err == cudaSuccess) err = cudaMemcpy(model->d_table, laid.data(), model->table_bytes, cudaMemcpyHostToDevice);
-    if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(reinterpret_cast<const void*>(geo->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(model->shared_bytes));
-    if (err == cudaSuccess)
-        err = cudaFuncSetAttribute(reinterpret_cast<const void*>(geo->fn_cj_same), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(model->shared_bytes));
-    if (err != cudaSuccess) {
-        cudaFree(model->d_table);
+    if (err != cudaSuccess || (!model->bulk.geo && !model->quad.geo)) {
+        cudaFree(model->bulk.d_table);
+        cudaFree(model->quad.d_table);
         delete model;
         (void)cudaGetLastError();
+        if (err == cudaErrorInvalidConfiguration)
+            return fail(MSV_ERR_MODEL_TOO_LONG, "emission table of a %zu-column model exceeds shared + tensor memory", columns);
         return fail(MSV_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(err));
     }
     *out = model;
@@ -591,7 +639,8 @@ int msv_cuda_model_destroy(msv_model* model) {
     db_release(model->workspace);
     {
         Device_guard guard(model->device);
-        cudaFree(model->d_table);
+        cudaFree(model->bulk.d_table);
+        cudaFree(model->quad.d_table);
     }
     delete model;
     return MSV_OK;
@@ -600,11 +649,12 @@ int msv_cuda_model_destroy(msv_model* model) {
 int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane,
                             int* tensor_columns_per_lane, int* threads_per_cta, size_t* shared_bytes) {
     if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
-    if (lanes_per_sequence) *lanes_per_sequence = model->geo->G;
-    if (columns_per_lane) *columns_per_lane = model->geo->K;
-    if (tensor_columns_per_lane) *tensor_columns_per_lane = model->geo->KT;
-    if (threads_per_cta) *threads_per_cta = model->geo->threads;
-    if (shared_bytes) *shared_bytes = model->shared_bytes;
+    const msv_model::Plan& plan = model->bulk.geo ? model->bulk : model->quad; // the throughput plan
+    if (lanes_per_sequence) *lanes_per_sequence = plan.geo->G;
+    if (columns_per_lane) *columns_per_lane = plan.geo->K;
+    if (tensor_columns_per_lane) *tensor_columns_per_lane = plan.geo->KT;
+    if (threads_per_cta) *threads_per_cta = plan.geo->threads;
+    if (shared_bytes) *shared_bytes = plan.shared_bytes;
     return MSV_OK;
 }
 

@@ -459,6 +459,208 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
     }
 }
 
+// =====================================================================================================================
+// Four warps per sequence ("quad" kernel): for FEW and LONG sequences (config 5: 2 048 sequences of 10-35 k residues,
+// the single-sequence API) and for models too long for one warp (LENG > 2 815).
+//
+// The row is serial in the sequence direction, so when there are fewer sequences than warp slots the makespan of the
+// warp-per-sequence kernel is the longest sequence at one sixteenth of an SM.  Here a group of four warps shares one
+// sequence: global lane gl = 32*(warp%4) + lane owns model columns gl*K+1 .. gl*K+K, so each warp holds a quarter of
+// the row.  Per row the four warps exchange two words through shared memory and meet at one named barrier:
+//   * the last column of each warp (boundary for the next warp's lane 0), double-buffered by row parity;
+//   * each warp's partial E (after CREDUX); every warp then reduces the four partial maxima and carries N/J/B itself.
+// The emission table is DISTRIBUTED rather than replicated: warp position q reads TMEM lane quarter q, which holds
+// only that quarter's slice, so shared memory + tensor memory together hold up to 20 x 5 631 emissions (483 KB) --
+// this is the "chunked" staging for models that do not fit shared memory alone.
+// =====================================================================================================================
+template <int K, int KT, int THREADS, bool CJ_SAME>
+__global__ void __launch_bounds__(THREADS, 1) msv_scan_quad_kernel(const Scan_params p) {
+    static_assert(KT == 0 || KT == 8 || KT == 16 || KT == 24, "TMEM columns per lane");
+    static_assert(THREADS % 128 == 0, "whole groups of four warps");
+    constexpr int KS = K - KT;
+    static_assert(K % 4 == 0 && KS >= 0 && KS % 4 == 0, "columns per lane");
+    constexpr uint32_t QUAD_BYTES = 128 * 16;         // one float4 per lane of the group
+    constexpr uint32_t ROW_BYTES = (KS / 4) * QUAD_BYTES;
+    constexpr uint32_t SMEM_TABLE_BYTES = kAlphabet * ROW_BYTES;
+    constexpr uint32_t COPY_CHUNK = 32768;
+    constexpr uint32_t TMEM_COLUMNS = 512;
+    constexpr int MAX_GROUPS = THREADS / 128;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t table_ready;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) float exchange[MAX_GROUPS][2][8]; // [group][row parity][4 partial E | 4 boundary columns]
+    __shared__ uint32_t ticket_slot[MAX_GROUPS];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wq = warp & 3;     // position inside the group == TMEM lane quarter
+    const int group = warp >> 2;
+
+    if (p.first_bad != nullptr && *p.first_bad != ~0ull) return;
+
+    if (threadIdx.x == 0) mbarrier_init(&table_ready, 1);
+    if constexpr (KT > 0) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                         "n"(TMEM_COLUMNS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if constexpr (KT > 0) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if constexpr (KS > 0) {
+        if (threadIdx.x == 0) {
+            mbarrier_expect_tx(&table_ready, SMEM_TABLE_BYTES);
+#pragma unroll 1
+            for (uint32_t at = 0; at + 1 <= SMEM_TABLE_BYTES; at += COPY_CHUNK) {
+                const uint32_t bytes = min(COPY_CHUNK, SMEM_TABLE_BYTES - at);
+                tma_bulk_load(smem_raw + at, reinterpret_cast<const unsigned char*>(p.table) + at, bytes, &table_ready);
+            }
+        }
+    }
+    uint32_t tmem_lane_base = 0;
+    if constexpr (KT > 0) {
+        tmem_lane_base = tmem_base_slot + ((static_cast<uint32_t>(wq) * 32u) << 16);
+        if (warp < 4) { // the first group fills all four quarters, each warp its own slice of the model
+            const float4* src =
+                reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(p.table) + SMEM_TABLE_BYTES);
+            for (int x = 0; x < kAlphabet; ++x) {
+#pragma unroll
+                for (int c = 0; c < KT / 8; ++c) {
+                    const int at = ((x * 128 + wq * 32 + lane) * KT + 8 * c) / 4;
+                    const float4 a = __ldg(src + at);
+                    const float4 b = __ldg(src + at + 1);
+                    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    tmem_store8(tmem_lane_base + x * KT + 8 * c, v);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if constexpr (KS > 0) mbarrier_wait(&table_ready, 0);
+
+    const uint32_t tab_lane = smem_u32(smem_raw) + (wq * 32 + lane) * 16;
+    const uint32_t xchg = smem_u32(&exchange[group][0][0]);
+    const int barrier_id = 1 + group;
+    const float NEG_INF = __int_as_float(0xff800000);
+    const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
+    auto group_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(barrier_id) : "memory"); };
+
+    for (;;) {
+        if (wq == 0 && lane == 0) ticket_slot[group] = atomicAdd(p.queue_head, 1u);
+        group_sync();
+        const uint32_t ticket = ticket_slot[group];
+        if (ticket >= p.n) break;
+        const uint32_t idx = __ldg(p.order + ticket);
+        const uint64_t begin = __ldg(p.offsets + idx);
+        const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
+        const float2 tr = __ldg(p.length_tr + (p.tr_by_sequence ? idx : len));
+        const float loop = tr.x, move = tr.y;
+
+        float m[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) m[j] = NEG_INF;
+        float J = NEG_INF, C = NEG_INF, N = 0.0f, B = move;
+        // boundary columns of "row 0" are -inf: written for parity 1 (row 1 reads parity (1-1)&1 ^ ... see below)
+        if (lane < 8) {
+            exchange[group][0][lane] = NEG_INF;
+            exchange[group][1][lane] = NEG_INF;
+        }
+        group_sync();
+
+        uint32_t parity = 0; // buffer written by the current row; the previous row wrote parity ^ 1
+        auto row = [&](const uint32_t x) {
+            float te[KT > 0 ? KT : 1];
+            if constexpr (KT > 0) tmem_load<KT>(tmem_lane_base + x * KT, te);
+            const uint32_t erow = tab_lane + x * ROW_BYTES;
+            const float bt = B + tBMk;
+            // left neighbour of this lane's first column: previous lane, or the previous warp's last column of the
+            // previous row (double-buffered in shared memory), or -inf for the very first column of the model
+            float left = __shfl_up_sync(0xffffffffu, m[K - 1], 1);
+            if (lane == 0) {
+                float carried;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(carried) : "r"(xchg + ((parity ^ 1u) * 8u + 4u + (wq > 0 ? wq - 1 : 0)) * 4u));
+                left = wq == 0 ? NEG_INF : carried;
+            }
+            float e = NEG_INF;
+#pragma unroll
+            for (int q = KS / 4 - 1; q >= 0; --q) {
+                const float4 ev = lds128(erow + q * QUAD_BYTES);
+                const int j = KT + 4 * q;
+                m[j + 3] = ev.w + fmaxf(m[j + 2], bt);
+                m[j + 2] = ev.z + fmaxf(m[j + 1], bt);
+                m[j + 1] = ev.y + fmaxf(m[j], bt);
+                m[j] = ev.x + fmaxf(j ? m[j > 0 ? j - 1 : 0] : left, bt);
+                e = fmaxf(fmaxf(e, m[j + 3]), m[j + 2]);
+                e = fmaxf(fmaxf(e, m[j + 1]), m[j]);
+            }
+            if constexpr (KT > 0) {
+                tmem_wait<KT>(te);
+#pragma unroll
+                for (int j = KT - 1; j >= 1; j -= 2) {
+                    m[j] = te[j] + fmaxf(m[j - 1], bt);
+                    m[j - 1] = te[j - 1] + fmaxf(j > 1 ? m[j > 1 ? j - 2 : 0] : left, bt);
+                    e = fmaxf(fmaxf(e, m[j]), m[j - 1]);
+                }
+            }
+            float warp_max;
+            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(warp_max) : "f"(e));
+            if (lane == 31) {
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(xchg + (parity * 8u + 4u + wq) * 4u), "f"(m[K - 1]) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(xchg + (parity * 8u + wq) * 4u), "f"(warp_max) : "memory");
+            }
+            group_sync();
+            float4 parts;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(parts.x), "=f"(parts.y), "=f"(parts.z), "=f"(parts.w)
+                         : "r"(xchg + parity * 32u));
+            const float E = fmaxf(fmaxf(fmaxf(parts.x, parts.y), parts.z), parts.w);
+            J = fmaxf(J + loop, E + tEJ);
+            if constexpr (!CJ_SAME) C = fmaxf(C + loop, E + tEC);
+            N = N + loop;
+            B = fmaxf(N, J) + move;
+            parity ^= 1u;
+        };
+
+        const uint32_t shift = (static_cast<uint32_t>(begin) & 3u) * 8u;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues + (begin & ~static_cast<uint64_t>(3)));
+        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        wp += 2;
+        const uint32_t quads = len >> 2;
+#pragma unroll 1
+        for (uint32_t i = 0; i < quads; ++i) {
+            const uint32_t word = __funnelshift_r(w0, w1, shift);
+            w0 = w1;
+            w1 = __ldg(wp);
+            ++wp;
+            row(__byte_perm(word, 0, 0x4440));
+            row(__byte_perm(word, 0, 0x4441));
+            row(__byte_perm(word, 0, 0x4442));
+            row(__byte_perm(word, 0, 0x4443));
+        }
+        uint32_t word = __funnelshift_r(w0, w1, shift);
+#pragma unroll 1
+        for (uint32_t r = len & 3u; r > 0; --r) {
+            row(word & 0xffu);
+            word >>= 8;
+        }
+        if (wq == 0 && lane == 0) p.scores[idx] = (CJ_SAME ? J : C) + move;
+    }
+
+    if constexpr (KT > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_slot), "n"(TMEM_COLUMNS) : "memory");
+    }
+}
+
 // ---- database preparation kernels -------------------------------------------------------------------------------
 // Validate residue codes (reference: unordered_map::at throws on a foreign letter, MSV_HMM.cpp:101) -- 16 B per thread.
 __global__ void db_validate_kernel(const uint4* __restrict__ words, uint64_t n_words16, uint64_t n_bytes, uint64_t base_position,

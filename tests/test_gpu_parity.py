@@ -101,7 +101,10 @@ def test_homologous_sequences_exercise_the_J_state(oracle):
                                        "32,56", "32,60", "32,88",
                                        # warp kernels: shared memory + KT tensor-memory columns per lane
                                        "32,4,0", "32,8,0", "32,8,8", "32,20,8", "32,24,16", "32,28,16", "32,44,0", "32,44,8",
-                                       "32,44,16", "32,44,24", "32,44,16,640", "32,64,16", "32,76,16", "32,88,16"])
+                                       "32,44,16", "32,44,24", "32,44,16,640", "32,64,16", "32,76,16", "32,76,24", "32,88,16",
+                                       # quad kernels: four warps (128 lanes) per sequence
+                                       "128,4,0", "128,8,8", "128,12,8", "128,16,16", "128,20,16", "128,28,16", "128,36,16",
+                                       "128,40,24", "128,44,24"])
 def test_every_kernel_geometry(oracle, geometry, monkeypatch):
     """Lanes-per-sequence x columns-per-lane (x tensor-memory columns) variants, forced through MSV_CUDA_GEOMETRY, all
     give reference bits."""
@@ -145,6 +148,47 @@ def test_all_models_default_geometry_small_batch(oracle):
         model, table, tr3 = device_model(oracle, name)
         want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
         assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist(), name
+
+
+def synthetic_model(rng, leng):
+    """A random model of `leng` columns in the reference's table layout [20][leng+1] (column 0 = -inf)."""
+    match = rng.dirichlet(np.full(20, 0.3), size=leng + 1).astype(np.float32)
+    match[0] = 0.0
+    return match
+
+
+@pytest.mark.parametrize("leng", [2816, 3000, 5631])
+def test_models_longer_than_one_warp(oracle, leng):
+    """LENG > 2815 does not fit one warp's registers: the four-warps-per-sequence kernel scans it, with the emission
+    table distributed over shared memory and tensor memory (20 x 5631 x 4 B = 450 KB at the upper limit)."""
+    rng = np.random.default_rng(leng)
+    match = synthetic_model(rng, leng)
+    table, tr3 = oracle.prepare(match)
+    model = msv.Model(_cabi.emission_table(match), *_cabi.model_transitions(leng + 1))
+    assert model.geometry["lanes_per_sequence"] == 128
+    seqs, codes, offsets = random_db(rng, 700 if leng < 5000 else 400, 0, 250)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+
+
+def test_model_beyond_on_chip_capacity_is_refused(oracle):
+    rng = np.random.default_rng(1)
+    match = synthetic_model(rng, 5700)
+    with pytest.raises(_cabi.MsvCudaError) as err:
+        msv.Model(_cabi.emission_table(match), *_cabi.model_transitions(5701))
+    assert err.value.status == _cabi.MSV_ERR_MODEL_TOO_LONG
+
+
+def test_few_long_sequences_use_four_warps_each(oracle):
+    """Below two sequences per warp slot the library switches to the quad plan by itself; same bits either way."""
+    model, table, tr3 = device_model(oracle, "1400.hmm")
+    rng = np.random.default_rng(6)
+    seqs = [rng.integers(0, 20, size=int(k), dtype=np.uint8) for k in rng.integers(500, 3000, size=40)]
+    codes, offsets = pack(seqs)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+    db = msv.Database(codes, offsets)
+    assert ubits(db.score(model)).tolist() == ubits(want).tolist()
 
 
 # ---- edge cases --------------------------------------------------------------------------------------------------
