@@ -423,11 +423,22 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
     db->longest = longest;
     if (n == 0) return MSV_OK;
 
-    // stages of roughly equal residue count; small batches are not split
-    const uint64_t min_stage_bytes = 4ull << 20;
-    const int stages = static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>(kMaxChunks, total / min_stage_bytes)));
+    // Stages grow geometrically: the first one is small so that the scan starts almost immediately, and every later
+    // upload (tens of GB/s over PCIe/C2C) finishes long before the scan of the stage before it (a few GB/s of residues).
     size_t bounds[kMaxChunks + 1];
-    if (int rc = msv_host_partition_by_cells(offsets, n, stages, bounds)) return rc;
+    int stages = 0;
+    bounds[0] = 0;
+    {
+        uint64_t stage_bytes = 2ull << 20, cut = 0;
+        while (stages < kMaxChunks - 1 && cut + stage_bytes + (stage_bytes >> 1) < total) {
+            cut += stage_bytes;
+            size_t q = static_cast<size_t>(std::lower_bound(offsets, offsets + n + 1, cut) - offsets);
+            q = std::min(q, n);
+            if (q > bounds[stages]) bounds[++stages] = q;
+            stage_bytes *= 4;
+        }
+        if (bounds[stages] < n || stages == 0) bounds[++stages] = n;
+    }
 
     MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy));
     MSV_CUDA_TRY(cudaMemsetAsync(db->d_residues + total, 0, msv::kResiduePadBytes + 16, copy));
@@ -534,13 +545,12 @@ int msv_host_partition_by_cells(const uint64_t* offsets, size_t n, int parts, si
     if (parts < 1 || !bounds || (n && !offsets)) return fail(MSV_ERR_INVALID_ARGUMENT, "bad partition request");
     bounds[0] = 0;
     const uint64_t base = n ? offsets[0] : 0, total = n ? offsets[n] - base : 0;
-    size_t q = 0;
     for (int part = 1; part < parts; ++part) {
-        // first sequence whose end passes the ideal cut; whichever side of it is closer to the cut wins
+        // first sequence boundary at or after the ideal cut (binary search); the nearer of it and its predecessor wins
         const uint64_t want = base + total / parts * part + (total % parts) * part / parts;
-        while (q < n && offsets[q + 1] <= want) ++q;
-        if (q < n && want - offsets[q] > offsets[q + 1] - want) ++q;
-        bounds[part] = q;
+        size_t q = static_cast<size_t>(std::lower_bound(offsets, offsets + n + 1, want) - offsets);
+        if (q > 0 && q <= n && offsets[q] - want > want - offsets[q - 1]) --q;
+        bounds[part] = std::min(q, n);
     }
     bounds[parts] = n;
     for (int part = 1; part <= parts; ++part) bounds[part] = std::max(bounds[part], bounds[part - 1]);

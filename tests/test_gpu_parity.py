@@ -233,6 +233,23 @@ def test_long_sequence_and_misaligned_offsets(oracle):
     assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
 
 
+def test_pipelined_upload_sizes_and_reuse(oracle):
+    """msv_cuda_score_batch uploads in stages that overlap with the scan; the workspace is reused and regrown between
+    calls.  Every size must equal the resident-database path bit for bit (and the oracle on a sample)."""
+    model, table, tr3 = device_model(oracle, "700.hmm")
+    rng = np.random.default_rng(21)
+    for n in (1, 7, 1000, 60_000, 300, 120_000, 5):
+        packed = msv.Packed_sequences.synthetic_swissprot_like(n, 1000 + n)
+        codes, offsets = packed.residues, packed.offsets
+        got = model.score_batch(codes, offsets)
+        resident = msv.Database(codes, offsets).score(model)
+        assert (ubits(got) == ubits(resident)).all(), n
+        sample = rng.choice(n, size=min(n, 50), replace=False)
+        sc, so = pack([codes[int(offsets[q]):int(offsets[q + 1])] for q in sample])
+        want = oracle.score_batch(table, tr3, sc, so, threads=CORES)
+        assert ubits(got[sample]).tolist() == ubits(want).tolist(), n
+
+
 # ---- size-independent properties at BASELINE sizes ----------------------------------------------------------------
 def test_full_size_properties_config4(oracle):
     """1400.hmm x 1M synthetic sequences (config 4): permutation equivariance, duplicate consistency, run-to-run
