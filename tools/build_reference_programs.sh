@@ -17,6 +17,11 @@ HOST=$PKG/host
 OUT=$ROOT/build
 CXX=${CXX:-g++}
 
+# this repository's own microsecond-resolution harness (no reference sources involved)
+mkdir -p "$OUT"
+$CXX -std=c++20 -O2 -Wall -Wextra -I"$HOST/algorithms" -I"$HOST/data_readers" -I"$ROOT/include" "$ROOT/tools/msv_bench.cpp" \
+    -o "$OUT/msv_bench" -L"$PKG" -lmsv_host -lmsv_cuda -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../hmm_fasta_viterbi_b200'
+
 [ -d "$REF/algorithms" ] || { echo "reference tree $REF not present; keeping prebuilt build/ (if any)"; exit 0; }
 mkdir -p "$OUT/algorithms" "$OUT/data_readers"
 cp -ru "$ROOT/fixtures/profile_HMMs" "$OUT/"
