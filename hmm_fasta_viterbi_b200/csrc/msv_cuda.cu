@@ -62,7 +62,8 @@ struct Geometry {
 };
 
 template <int G, int K> constexpr Geometry generic_entry() {
-    return Geometry{G, K, -1, threads_for(K), msv::msv_scan_kernel<G, K, threads_for(K)>, msv::msv_scan_kernel<G, K, threads_for(K)>};
+    return Geometry{G, K, -1, threads_for(K), msv::msv_scan_kernel<G, K, threads_for(K), false>,
+                    msv::msv_scan_kernel<G, K, threads_for(K), true>};
 }
 template <int K, int KT> constexpr Geometry warp_entry() {
     return Geometry{32, K, KT, warp_threads_for(K, KT), msv::msv_scan_warp_kernel<K, KT, warp_threads_for(K, KT), false>,
@@ -115,7 +116,7 @@ const Geometry* choose_geometry(size_t columns) {
     if (const char* env = std::getenv("MSV_CUDA_GEOMETRY")) {
         int G = 0, K = 0, KT = -1, T = 0;
         const int got = std::sscanf(env, "%d,%d,%d,%d", &G, &K, &KT, &T);
-        if (got == 2 && static_cast<size_t>(G) * K >= columns)
+        if (got == 2 && static_cast<size_t>(G) * K > columns)
             if (const Geometry* g = find_geometry(G, K, -1)) return g;
         if (got >= 3 && static_cast<size_t>(G) * K > columns)
             if (const Geometry* g = find_geometry(G, K, KT, T)) return g;
@@ -127,6 +128,13 @@ const Geometry* choose_geometry(size_t columns) {
     if (K > msv::kMaxColumnsPerLane) return nullptr;
     const int KT = K >= 72 ? 24 : K >= 16 ? 16 : K >= 8 ? 8 : 0;
     return find_geometry(32, K, KT);
+}
+
+// Eight lanes per sequence (four sequences per warp) pays off for short models: measured on B200
+// (profiles/r01/sweep_generic_v3.jsonl) it beats the warp plan for LENG 200-447 when there are enough sequences.
+const Geometry* choose_octet_geometry(size_t columns) {
+    const int K = std::max(4, round_up4((columns + 1 + 7) / 8)); // 8*K > columns
+    return (columns >= 150 && K <= 56) ? find_geometry(8, K, -1) : nullptr;
 }
 
 // Four warps per sequence: the plan for few/long sequences and for models beyond one warp's registers.
@@ -187,7 +195,8 @@ struct msv_model {
         size_t shared_bytes = 0; // dynamic shared memory of the scan kernel
         float4* d_table = nullptr;
     };
-    Plan bulk;  // many sequences: one warp (or a lane group) per sequence
+    Plan bulk;  // many sequences: one warp per sequence (or whatever MSV_CUDA_GEOMETRY forces)
+    Plan octet; // short models and enough sequences to balance 4x more slots: eight lanes per sequence (may be absent)
     Plan quad;  // few or very long sequences, single-sequence calls: four warps per sequence (may be absent)
     bool forced = false; // MSV_CUDA_GEOMETRY was given: always use `bulk`
     float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
@@ -353,19 +362,29 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
     return db_read_validation(db, residues, stream);
 }
 
-// Which plan scans `count` sequences: the four-warp plan when there are too few sequences to fill the warp slots of the
-// bulk plan (the makespan would be one long sequence on a sixteenth of an SM), or when the model has no bulk plan.
-const msv_model::Plan& pick_plan(const msv_model* model, size_t count) {
+// Which plan scans `count` sequences holding `residues` residues, the longest of them `longest`:
+//   * the four-warp plan when there are too few sequences to fill the warp slots of the bulk plan (the makespan would
+//     be one long sequence on a sixteenth of an SM), or when the model has no bulk plan;
+//   * the eight-lane plan for short models when the average slot still gets about as many rows as the longest
+//     sequence has (it has four times more slots than the warp plan; with less work per slot the longest sequence
+//     alone sets the makespan -- measured break-even on B200, profiles/r01/sweep_generic_v3.jsonl);
+//   * else one warp per sequence.
+const msv_model::Plan& pick_plan(const msv_model* model, size_t count, uint64_t residues, uint64_t longest) {
     if (!model->bulk.geo) return model->quad;
-    if (model->forced || !model->quad.geo) return model->bulk;
-    const size_t bulk_slots = static_cast<size_t>(model->sm_count) * (model->bulk.geo->threads / model->bulk.geo->G);
-    return count < 2 * bulk_slots ? model->quad : model->bulk;
+    if (model->forced) return model->bulk;
+    const auto slots = [&](const msv_model::Plan& plan) {
+        return static_cast<uint64_t>(model->sm_count) * (plan.geo->threads / plan.geo->G);
+    };
+    if (model->quad.geo && count < 2 * slots(model->bulk)) return model->quad;
+    if (model->octet.geo && 4 * (residues / slots(model->octet)) >= 3 * std::max<uint64_t>(longest, 1)) return model->octet;
+    return model->bulk;
 }
 
 // One launch of the scan over sequences [first, first+count) of `db`; scores go to d_scores[first ..).
-int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, int queue_slot, float* d_scores, cudaStream_t stream) {
+int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64_t residues, int queue_slot, float* d_scores,
+                cudaStream_t stream) {
     if (count == 0) return MSV_OK;
-    const msv_model::Plan& plan = pick_plan(model, count);
+    const msv_model::Plan& plan = pick_plan(model, count, residues, db->longest);
     const Geometry* geo = plan.geo;
     msv::Scan_params p{};
     p.table = plan.d_table;
@@ -449,7 +468,7 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
         MSV_CUDA_TRY(cudaEventRecord(db->stage_copied[s], copy));
         MSV_CUDA_TRY(cudaStreamWaitEvent(compute, db->stage_copied[s], 0));
         if (int rc = db_prepare_range(db, first, last - first, begin, end, longest, compute)) return rc;
-        if (int rc = launch_scan(model, db, first, last - first, s, db->d_scores, compute)) return rc;
+        if (int rc = launch_scan(model, db, first, last - first, end - begin, s, db->d_scores, compute)) return rc;
     }
     MSV_CUDA_TRY(cudaMemcpyAsync(scores_host, db->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, compute));
     return db_read_validation(db, residues, compute);
@@ -631,8 +650,11 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         const cudaError_t quad_err = build(quad_geo, model->quad);
         if (!bulk_geo) err = quad_err; // the quad plan is optional unless it is the only one
     }
+    if (err == cudaSuccess && bulk_geo && !forced)
+        if (const Geometry* octet_geo = choose_octet_geometry(columns)) (void)build(octet_geo, model->octet); // optional
     if (err != cudaSuccess || (!model->bulk.geo && !model->quad.geo)) {
         cudaFree(model->bulk.d_table);
+        cudaFree(model->octet.d_table);
         cudaFree(model->quad.d_table);
         delete model;
         (void)cudaGetLastError();
@@ -650,6 +672,7 @@ int msv_cuda_model_destroy(msv_model* model) {
     {
         Device_guard guard(model->device);
         cudaFree(model->bulk.d_table);
+        cudaFree(model->octet.d_table);
         cudaFree(model->quad.d_table);
     }
     delete model;
@@ -706,7 +729,7 @@ int msv_cuda_db_score_device(msv_model* model, msv_db* db, float* scores_device,
     if (db->n && !scores_device) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_device is NULL");
     Device_guard guard(model->device);
     MSV_CUDA_TRY(guard.status);
-    return launch_scan(model, db, 0, db->n, 0, scores_device, static_cast<cudaStream_t>(cuda_stream));
+    return launch_scan(model, db, 0, db->n, db->total, 0, scores_device, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host) {
@@ -715,7 +738,7 @@ int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host) {
     if (db->n && !scores_host) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_host is NULL");
     Device_guard guard(model->device);
     MSV_CUDA_TRY(guard.status);
-    if (int rc = launch_scan(model, db, 0, db->n, 0, db->d_scores, nullptr)) return rc;
+    if (int rc = launch_scan(model, db, 0, db->n, db->total, 0, db->d_scores, nullptr)) return rc;
     if (db->n) MSV_CUDA_TRY(cudaMemcpy(scores_host, db->d_scores, db->n * sizeof(float), cudaMemcpyDeviceToHost));
     return MSV_OK;
 }

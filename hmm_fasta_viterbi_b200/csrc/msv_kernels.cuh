@@ -96,12 +96,26 @@ template <int G> __device__ __forceinline__ float group_max(float v) {
     }
 }
 
-// ---- the scan ---------------------------------------------------------------------------------------------------
-template <int G, int K, int THREADS>
+// ---- shared-memory loads with explicit 32-bit addresses -----------------------------------------------------------
+__device__ __forceinline__ float4 lds128(uint32_t shared_address) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(shared_address));
+    return v;
+}
+
+// ---- the scan, lane-group family: G = 8, 16 or 32 lanes per sequence, whole table in shared memory ------------------
+// A warp scans 32/G sequences at once; every group pulls its own sequences from the queue.  Rows are executed in
+// warp-uniform chunks (the minimum over the groups of their remaining rows), so the row loop itself never diverges;
+// retiring a sequence and fetching the next one happens between chunks.  Per-row bookkeeping is shared by the 32/G
+// sequences of the warp, which is what makes this family the faster one for short models.
+// The host guarantees G*K > model columns: the last column of a group's last lane is -inf padding, so the rotating
+// shuffle hands lane 0 of each group the -inf of the dummy column M0 (same trick as in the warp kernel below).
+template <int G, int K, int THREADS, bool CJ_SAME>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params p) {
     static_assert(G == 8 || G == 16 || G == 32, "lanes per sequence");
     static_assert(K % 4 == 0 && K >= 4 && K <= kMaxColumnsPerLane, "columns per lane");
-    constexpr int ROW4 = (K / 4) * G; // float4 elements per residue row of the table
+    constexpr uint32_t ROW_BYTES = (K / 4) * G * 16; // bytes per residue row of the table
+    constexpr uint32_t QUAD_BYTES = G * 16;
     constexpr uint32_t COPY_CHUNK = 32768;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -125,7 +139,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
-    const float4* tab_lane = reinterpret_cast<const float4*>(smem_raw) + gl;
+    const int left_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1)); // rotate inside the group
+    const uint32_t tab_lane = smem_u32(smem_raw) + gl * 16;
     const float NEG_INF = __int_as_float(0xff800000);
     const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
 
@@ -143,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
         // ---- retire finished sequences, pull new ones (group-uniform control flow) ----
         while (remaining == 0 && !done) {
             if (active) {
-                if (gl == 0) p.scores[idx] = C + move; // MSV_HMM.cpp:112
+                if (gl == 0) p.scores[idx] = (CJ_SAME ? J : C) + move; // MSV_HMM.cpp:112
                 active = false;
             }
             uint32_t ticket = 0;
@@ -186,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
 
 #pragma unroll 1
         for (uint32_t t = 0; t < steps; ++t) {
-            const uint32_t x = buf & 0xffu;
+            const uint32_t erow = tab_lane + (buf & 0xffu) * ROW_BYTES;
             buf >>= 8;
             if (--have == 0) {
                 buf = nextw;
@@ -194,29 +209,27 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
                 if (!done) nextw = __ldg(wp);
                 ++wp;
             }
-            const float4* e = tab_lane + x * ROW4;
             const float bt = B + tBMk; // MSV_HMM.cpp:103, the B -> M_k entry
-            float left = __shfl_up_sync(0xffffffffu, m[K - 1], 1, G);
-            if (gl == 0) left = NEG_INF; // column 0 (dummy M0) stays -inf
+            const float left = __shfl_sync(0xffffffffu, m[K - 1], left_lane);
 
-            float e0 = NEG_INF, e1 = NEG_INF;
+            float e = NEG_INF;
 #pragma unroll
             for (int q = K / 4 - 1; q >= 0; --q) {
-                const float4 ev = e[q * G];
+                const float4 ev = lds128(erow + q * QUAD_BYTES);
                 const int j = 4 * q;
                 m[j + 3] = ev.w + fmaxf(m[j + 2], bt);
                 m[j + 2] = ev.z + fmaxf(m[j + 1], bt);
                 m[j + 1] = ev.y + fmaxf(m[j], bt);
-                m[j] = ev.x + fmaxf(q ? m[j - 1] : left, bt);
-                e0 = fmaxf(fmaxf(e0, m[j + 3]), m[j + 2]); // MSV_HMM.cpp:104
-                e1 = fmaxf(fmaxf(e1, m[j + 1]), m[j]);
+                m[j] = ev.x + fmaxf(q ? m[j > 0 ? j - 1 : 0] : left, bt);
+                e = fmaxf(fmaxf(e, m[j + 3]), m[j + 2]); // MSV_HMM.cpp:104
+                e = fmaxf(fmaxf(e, m[j + 1]), m[j]);
             }
-            const float E = group_max<G>(fmaxf(e0, e1));
+            const float E = group_max<G>(e);
 
-            J = fmaxf(J + loop, E + tEJ);   // MSV_HMM.cpp:107
-            C = fmaxf(C + loop, E + tEC);   // MSV_HMM.cpp:108
-            N = N + loop;                   // MSV_HMM.cpp:109
-            B = fmaxf(N + move, J + move);  // MSV_HMM.cpp:110
+            J = fmaxf(J + loop, E + tEJ);                         // MSV_HMM.cpp:107
+            if constexpr (!CJ_SAME) C = fmaxf(C + loop, E + tEC); // MSV_HMM.cpp:108
+            N = N + loop;                                         // MSV_HMM.cpp:109
+            B = fmaxf(N, J) + move; // MSV_HMM.cpp:110: max(N+move, J+move) == max(N, J)+move exactly (rounding is monotone)
         }
     }
 }
@@ -234,12 +247,6 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
 // it is in flight, tcgen05.wait::ld, then the TMEM columns.  The address must be warp-uniform, which is why this
 // variant exists for G == 32 only (all lanes of the warp scan the same residue).
 // =====================================================================================================================
-__device__ __forceinline__ float4 lds128(uint32_t shared_address) {
-    float4 v;
-    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(shared_address));
-    return v;
-}
-
 __device__ __forceinline__ void tmem_store8(uint32_t taddr, const float* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]),
                  "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])

@@ -111,7 +111,7 @@ def test_every_kernel_geometry(oracle, geometry, monkeypatch):
     parts = [int(v) for v in geometry.split(",")]
     G, K = parts[0], parts[1]
     KT = parts[2] if len(parts) > 2 else -1
-    limit = G * K - (1 if KT >= 0 else 0)  # the warp kernel needs one padding column
+    limit = G * K - 1  # every kernel needs one padding column at the end of the row
     fits = [n for n in model_files() if int(n.split(".")[0]) <= limit]
     if not fits:
         pytest.skip("no fixture model fits this geometry")
@@ -189,6 +189,20 @@ def test_few_long_sequences_use_four_warps_each(oracle):
     assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
     db = msv.Database(codes, offsets)
     assert ubits(db.score(model)).tolist() == ubits(want).tolist()
+
+
+def test_short_model_large_database_uses_eight_lanes_per_sequence(oracle):
+    """300.hmm x 150k sequences: enough rows per slot for the eight-lane plan to be picked automatically."""
+    model, table, tr3 = device_model(oracle, "300.hmm")
+    packed = msv.Packed_sequences.synthetic_swissprot_like(150_000, 300)
+    codes, offsets = packed.residues, packed.offsets
+    got = msv.Database(codes, offsets).score(model)
+    rng = np.random.default_rng(300)
+    sample = rng.choice(len(packed), size=500, replace=False)
+    sc, so = pack([codes[int(offsets[q]):int(offsets[q + 1])] for q in sample])
+    want = oracle.score_batch(table, tr3, sc, so, threads=CORES)
+    assert ubits(got[sample]).tolist() == ubits(want).tolist()
+    assert (ubits(model.score_batch(codes, offsets)) == ubits(got)).all()
 
 
 # ---- edge cases --------------------------------------------------------------------------------------------------
