@@ -304,9 +304,19 @@ def main() -> None:
         achieved = kernel_gcups * LANE_OPS_PER_CELL / 1e3
         hbm_peak = peaks.get("hbm_gbs") or 6650.0
         hbm_bytes = float(offsets[-1]) + 8.0 * (n_local + 1) + 4.0 * n_local * 2  # residues + offsets + order + scores
+        # DRAM traffic per launch comes from the committed ncu --set full capture of this same workload (it cannot be
+        # measured live without a profiler); null when the workload differs from the captured one.
+        traffic, traffic_source = None, None
+        try:
+            with open(os.path.join(REPO, "profiles", "roofline_traffic.json")) as f:
+                captured = json.load(f)
+            if captured.get("workload") == f"{args.model} x {args.sequences} sequences" and world == 1:
+                traffic, traffic_source = captured["traffic_bytes_per_launch"], captured["source"]
+        except OSError:
+            pass
         roofline = {
-            "bound": "fp32_alu", "kernel": "msv_scan_kernel", "achieved": achieved, "peak": alu_peak, "unit": "Tlaneop/s",
-            "frac": achieved / alu_peak, "traffic": None,
+            "bound": "fp32_alu", "kernel": "msv_scan_warp_kernel", "achieved": achieved, "peak": alu_peak, "unit": "Tlaneop/s",
+            "frac": achieved / alu_peak, "traffic": traffic, "traffic_source": traffic_source, "algorithmic_hbm_bytes": hbm_bytes,
             "peak_source": f"{sms} SMs x 128 fp32 lanes x {sm_max_mhz:.0f} MHz (max SM clock); 3 lane-ops per cell",
             "kernel_ms": kernel_ms, "kernel_gcups": kernel_gcups, "gcups_at_alu_roofline": alu_peak * 1e3 / LANE_OPS_PER_CELL,
             "smem_ceiling_gcups": sms * 32 * sm_max_mhz * 1e6 / 1e9,
