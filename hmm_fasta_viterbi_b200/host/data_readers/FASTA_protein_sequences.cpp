@@ -3,7 +3,7 @@
 #include <array>
 #include <fstream>
 #include <iostream>
-#include <iterator>
+#include <algorithm>
 #include <string_view>
 
 // Record rules (behaviour of the reference's data_readers/FASTA_protein_sequences.cpp:9-44):
@@ -33,7 +33,10 @@ FASTA_protein_sequences::FASTA_protein_sequences(const std::string& file_path) {
         std::cout << "Failed to open " << file_path << '\n';
         return;
     }
-    const auto text = std::string(std::istreambuf_iterator<char>(file), std::istreambuf_iterator<char>());
+    file.seekg(0, std::ios::end);
+    auto text = std::string(static_cast<size_t>(std::max<std::streamoff>(file.tellg(), 0)), '\0');
+    file.seekg(0, std::ios::beg);
+    file.read(text.data(), static_cast<std::streamsize>(text.size()));
     auto rest = std::string_view(text);
 
     auto record_open = false;

@@ -1,9 +1,14 @@
 #include "Packed_sequences.hpp"
 
-#include <cstdio>
+#include <algorithm>
 #include <cstring>
-#include <memory>
 #include <stdexcept>
+#include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "msv_cuda.h"
 
@@ -34,60 +39,134 @@ Packed_sequences Packed_sequences::from_sequences(const Protein_sequences& seque
     return packed;
 }
 
+namespace {
+
+// Result of parsing one slice of a FASTA file that starts at a record header.
+struct Parsed_slice {
+    std::vector<uint8_t> residues;
+    std::vector<uint64_t> lengths;
+    size_t rejected = 0;
+};
+
+// letter -> code, 0xff for everything else
+struct Code_table {
+    uint8_t of[256];
+    Code_table() {
+        std::memset(of, 0xff, sizeof of);
+        for (int i = 0; i < MSV_ALPHABET; ++i) of[static_cast<unsigned char>(letters[i])] = static_cast<uint8_t>(i);
+    }
+};
+
+// Parse [begin, end): `begin` points at a '>' that starts a line (or begin == end).  Record rules as in
+// FASTA_protein_sequences.cpp: header text dropped, other lines appended verbatim, a record with any non-letter is
+// dropped whole.  (The reference's filter lets a '#' inside a record through, FASTA_protein_sequences.cpp:30, and its
+// scorer then throws on it, MSV_HMM.cpp:101; here such a record is rejected when read.)
+void parse_slice(const char* begin, const char* end, Parsed_slice& out) {
+    static const Code_table table;
+    out.residues.resize(static_cast<size_t>(end - begin)); // upper bound; shrunk at the end
+    auto* dst = out.residues.data();
+    auto* record_start = dst;
+    auto open = false;
+    uint8_t poison = 0;
+    const auto close_record = [&] {
+        if (!open) return;
+        if (poison & 0x80) {
+            dst = record_start;
+            ++out.rejected;
+        } else {
+            out.lengths.push_back(static_cast<uint64_t>(dst - record_start));
+        }
+    };
+    for (const char* line = begin; line < end;) {
+        const auto* eol = static_cast<const char*>(std::memchr(line, '\n', static_cast<size_t>(end - line)));
+        const char* stop = eol ? eol : end;
+        if (line < stop && *line == '>') {
+            close_record();
+            open = true;
+            poison = 0;
+            record_start = dst;
+        } else if (open) {
+            for (const char* c = line; c < stop; ++c) {
+                const auto code = table.of[static_cast<unsigned char>(*c)];
+                *dst++ = code;
+                poison |= code;
+            }
+        }
+        line = stop + 1;
+    }
+    close_record();
+    out.residues.resize(static_cast<size_t>(dst - out.residues.data()));
+}
+
+} // namespace
+
+// The file is mapped, cut at record boundaries into one slice per hardware thread, parsed in parallel and stitched
+// together with a prefix sum -- the reference's reader is a single-threaded getline loop plus a hash lookup per
+// character (FASTA_protein_sequences.cpp:18-41), which would dominate the end-to-end time of a TCUPS scan.
 Packed_sequences Packed_sequences::from_fasta_file(const std::string& file_path, size_t* rejected) {
     auto packed = Packed_sequences();
     if (rejected) *rejected = 0;
-    auto file = std::unique_ptr<std::FILE, int (*)(std::FILE*)>(std::fopen(file_path.c_str(), "rb"), &std::fclose);
-    if (!file) throw std::runtime_error("Failed to open " + file_path);
-
-    // letter -> code, 0xff for everything else ('\n' is handled before the lookup)
-    uint8_t code_of[256];
-    std::memset(code_of, 0xff, sizeof code_of);
-    for (int i = 0; i < MSV_ALPHABET; ++i) code_of[static_cast<unsigned char>(letters[i])] = static_cast<uint8_t>(i);
-
-    auto chunk = std::vector<char>(1 << 20);
-    auto in_header = false, line_start = true, open = false, poisoned = false;
-    auto record_begin = size_t(0);
-    const auto close_record = [&] {
-        if (!open) return;
-        if (poisoned) {
-            packed.residues.resize(record_begin);
-            if (rejected) ++*rejected;
-        } else {
-            packed.offsets.push_back(packed.residues.size());
-        }
-        open = poisoned = false;
-    };
-    for (;;) {
-        const auto got = std::fread(chunk.data(), 1, chunk.size(), file.get());
-        if (got == 0) break;
-        packed.residues.reserve(packed.residues.size() + got);
-        for (size_t i = 0; i < got; ++i) {
-            const auto c = chunk[i];
-            if (c == '\n') {
-                in_header = false;
-                line_start = true;
-                continue;
-            }
-            if (line_start && c == '>') {
-                close_record();
-                open = true;
-                record_begin = packed.residues.size();
-                in_header = true;
-            } else if (!in_header && open) {
-                // Any non-letter poisons the record.  (The reference's filter lets a '#' inside a record through,
-                // FASTA_protein_sequences.cpp:30, and its scorer then throws on it, MSV_HMM.cpp:101; here such a
-                // record is rejected when read.)
-                const auto code = code_of[static_cast<unsigned char>(c)];
-                if (code == 0xff)
-                    poisoned = true;
-                else
-                    packed.residues.push_back(code);
-            }
-            line_start = false;
-        }
+    const int fd = ::open(file_path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("Failed to open " + file_path);
+    struct stat info {};
+    if (::fstat(fd, &info) != 0 || info.st_size == 0) {
+        ::close(fd);
+        if (info.st_size == 0) return packed;
+        throw std::runtime_error("Failed to stat " + file_path);
     }
-    close_record();
+    const auto size = static_cast<size_t>(info.st_size);
+    void* mapping = ::mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (mapping == MAP_FAILED) throw std::runtime_error("Failed to map " + file_path);
+    const auto* text = static_cast<const char*>(mapping);
+    const char* const text_end = text + size;
+
+    // next record header at or after `from`: a '>' at the start of a line
+    const auto next_header = [&](const char* from) -> const char* {
+        if (from == text && *from == '>') return from;
+        for (const char* p = from; p < text_end;) {
+            const auto* nl = static_cast<const char*>(std::memchr(p, '\n', static_cast<size_t>(text_end - p)));
+            if (!nl || nl + 1 >= text_end) return text_end;
+            if (nl[1] == '>') return nl + 1;
+            p = nl + 1;
+        }
+        return text_end;
+    };
+
+    const auto workers = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), size / (4u << 20) + 1));
+    auto cuts = std::vector<const char*>(workers + 1, text_end);
+    cuts[0] = next_header(text);
+    for (size_t w = 1; w < workers; ++w) cuts[w] = std::max(cuts[w - 1], next_header(text + size / workers * w));
+    auto slices = std::vector<Parsed_slice>(workers);
+    {
+        auto pool = std::vector<std::thread>();
+        for (size_t w = 1; w < workers; ++w) pool.emplace_back([&, w] { parse_slice(cuts[w], cuts[w + 1], slices[w]); });
+        parse_slice(cuts[0], cuts[1], slices[0]);
+        for (auto& th : pool) th.join();
+    }
+    ::munmap(mapping, size);
+
+    auto total_residues = size_t(0), total_records = size_t(0);
+    for (const auto& sl : slices) {
+        total_residues += sl.residues.size();
+        total_records += sl.lengths.size();
+        if (rejected) *rejected += sl.rejected;
+    }
+    packed.residues.resize(total_residues);
+    packed.offsets.resize(total_records + 1);
+    auto residue_at = size_t(0), record_at = size_t(0);
+    auto copies = std::vector<std::thread>();
+    for (auto& sl : slices) {
+        auto running = static_cast<uint64_t>(residue_at);
+        for (const auto len : sl.lengths) {
+            running += len;
+            packed.offsets[++record_at] = running;
+        }
+        if (!sl.residues.empty())
+            copies.emplace_back([&packed, &sl, residue_at] { std::memcpy(packed.residues.data() + residue_at, sl.residues.data(), sl.residues.size()); });
+        residue_at += sl.residues.size();
+    }
+    for (auto& th : copies) th.join();
     return packed;
 }
 

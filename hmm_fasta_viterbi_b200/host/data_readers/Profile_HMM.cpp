@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
-#include <iterator>
+#include <algorithm>
 
 // Parsing contract (behaviour of the reference's data_readers/Profile_HMM.cpp:8-122, restated):
 //   * the file is scanned strictly forward: NAME, LENG, three STATS lines, COMPO, then nodes 1..LENG;
@@ -92,7 +92,10 @@ Profile_HMM::Profile_HMM(const std::string& file_path) {
         std::cout << "Failed to open " << file_path << '\n';
         return;
     }
-    const auto text = std::string(std::istreambuf_iterator<char>(file), std::istreambuf_iterator<char>());
+    file.seekg(0, std::ios::end);
+    auto text = std::string(static_cast<size_t>(std::max<std::streamoff>(file.tellg(), 0)), '\0');
+    file.seekg(0, std::ios::beg);
+    file.read(text.data(), static_cast<std::streamsize>(text.size()));
     if (!parse(text)) std::cout << "Incomplete profile HMM in " << file_path << '\n';
 }
 
