@@ -29,6 +29,7 @@ DECLARED_SYMBOLS = (
     "msv_cuda_model_create", "msv_cuda_model_destroy", "msv_cuda_model_geometry",
     "msv_cuda_db_create", "msv_cuda_db_destroy", "msv_cuda_db_info",
     "msv_cuda_db_score_device", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
+    "msv_cuda_db_filter_device",
     "msv_cuda_launch_count",
 )
 
@@ -73,6 +74,7 @@ lib.msv_cuda_db_score_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c
 lib.msv_cuda_db_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.msv_cuda_score_sequence.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, _fp]
+lib.msv_cuda_db_filter_device.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_launch_count.restype = C.c_uint64
 lib.msv_cuda_launch_count.argtypes = [C.c_int]
 for _name in DECLARED_SYMBOLS:
@@ -218,6 +220,11 @@ class Database:
     def score_device(self, model: Model, scores_device, stream: int = 0) -> None:
         """Asynchronous scan into a device buffer (torch CUDA tensor or raw pointer) on `stream`."""
         check(lib.msv_cuda_db_score_device(model.handle, self.handle, _ptr(scores_device), stream))
+
+    def filter_device(self, scores_device, mu: float, lam: float, bits_device=None, pvalues_device=None, stream: int = 0) -> None:
+        """Bit scores and Gumbel P-values (HMMER3 MSV filter conventions) from raw scores resident on the device."""
+        check(lib.msv_cuda_db_filter_device(self.handle, _ptr(scores_device), float(mu), float(lam), _ptr(bits_device),
+                                            _ptr(pvalues_device), stream))
 
     def close(self) -> None:
         if getattr(self, "handle", None):

@@ -756,6 +756,22 @@ int msv_cuda_score_batch(msv_model* model, const uint8_t* residues, const uint64
     return score_batch_pipelined(model, model->workspace, residues, offsets, n, scores_host);
 }
 
+int msv_cuda_db_filter_device(msv_db* db, const float* scores_device, float mu, float lambda, float* bits_device,
+                              float* pvalues_device, void* cuda_stream) {
+    if (!db) return fail(MSV_ERR_INVALID_ARGUMENT, "db is NULL");
+    if (db->n == 0) return MSV_OK;
+    if (!scores_device) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_device is NULL");
+    if (!(lambda > 0.0f)) return fail(MSV_ERR_INVALID_ARGUMENT, "lambda must be positive");
+    Device_guard guard(db->device);
+    MSV_CUDA_TRY(guard.status);
+    const uint32_t n32 = static_cast<uint32_t>(db->n);
+    msv::msv_filter_statistics_kernel<<<(n32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+        scores_device, db->d_offsets, n32, static_cast<double>(mu), static_cast<double>(lambda), bits_device, pvalues_device);
+    ++g_launches;
+    MSV_CUDA_TRY(cudaGetLastError());
+    return MSV_OK;
+}
+
 int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score) {
     if (!score) return fail(MSV_ERR_INVALID_ARGUMENT, "score is NULL");
     const uint64_t offsets[2] = {0, length};

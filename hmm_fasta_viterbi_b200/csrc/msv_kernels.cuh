@@ -742,4 +742,18 @@ __global__ void db_scatter_kernel(const uint64_t* __restrict__ offsets, uint32_t
     order[atomicAdd(cursor + b, 1u)] = q;
 }
 
+// ---- MSV filter statistics: raw score -> bit score -> Gumbel P-value (HMMER3 conventions) ----------------------------
+__global__ void msv_filter_statistics_kernel(const float* __restrict__ scores, const uint64_t* __restrict__ offsets, uint32_t n,
+                                             double mu, double lambda, float* __restrict__ bits_out, float* __restrict__ p_out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const double L = static_cast<double>(offsets[q + 1] - offsets[q]);
+    const double null1 = L * log(L / (L + 1.0)) + log(1.0 / (L + 1.0));
+    const double bits = (static_cast<double>(scores[q]) - null1) / 0.69314718055994530942;
+    const double ey = -exp(-lambda * (bits - mu));
+    const double p = fabs(ey) < 5e-9 ? -ey : 1.0 - exp(ey);
+    if (bits_out) bits_out[q] = static_cast<float>(bits);
+    if (p_out) p_out[q] = static_cast<float>(p);
+}
+
 } // namespace msv

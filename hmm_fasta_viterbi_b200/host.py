@@ -69,6 +69,7 @@ lib.msvh_msv_length.argtypes = [_vp]
 lib.msvh_msv_run_on_sequence.argtypes = [_vp, C.c_char_p, C.POINTER(C.c_float)]
 lib.msvh_msv_parallel_run_on_sequence.argtypes = [_vp, C.c_char_p, C.c_int, C.POINTER(C.c_float)]
 lib.msvh_msv_parallel_run_on_packed.argtypes = [_vp, _vp, _f32]
+lib.msvh_msv_parallel_run_on_packed_devices.argtypes = [_vp, _vp, C.POINTER(C.c_int), C.c_int, _f32]
 
 
 def _raise(status: int) -> None:
@@ -201,11 +202,16 @@ class MSV_HMM:
             _raise(status)
         return np.float32(out.value)
 
-    def parallel_run_on_sequences(self, database) -> np.ndarray:
+    def parallel_run_on_sequences(self, database, devices=None) -> np.ndarray:
+        """Whole database in one call; `devices` (list of GPU indices) spreads it over several GPUs from this process."""
         if isinstance(database, FASTA_protein_sequences):
             database = Packed_sequences.from_fasta(database)
         out = np.empty(max(len(database), 1), np.float32)
-        status = lib.msvh_msv_parallel_run_on_packed(self._h, database._h, out)
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            status = lib.msvh_msv_parallel_run_on_packed_devices(self._h, database._h, arr, len(devices), out)
+        else:
+            status = lib.msvh_msv_parallel_run_on_packed(self._h, database._h, out)
         if status:
             _raise(status)
         return out[: len(database)]

@@ -2,6 +2,7 @@
 
 #include <limits>
 #include <stdexcept>
+#include <thread>
 
 #include "msv_cuda.h"
 
@@ -95,6 +96,39 @@ std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Packed_sequences
     const auto status = msv_cuda_score_batch(on_device(), database.residues.data(), database.offsets.data(), database.size(),
                                              scores.data());
     if (status != MSV_OK) throw_last_error("MSV_HMM::parallel_run_on_sequences", status);
+    return scores;
+}
+
+std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Packed_sequences& database, const std::vector<int>& devices) {
+    if (devices.empty()) throw std::invalid_argument("MSV_HMM::parallel_run_on_sequences: no devices given");
+    const auto parts = static_cast<int>(devices.size());
+    const auto bounds = database.cell_balanced_bounds(parts);
+    auto scores = std::vector<Log_score>(database.size());
+    auto failures = std::vector<std::string>(devices.size());
+    auto workers = std::vector<std::thread>();
+    for (int part = 0; part < parts; ++part) {
+        workers.emplace_back([&, part] {
+            try {
+                auto replica = MSV_HMM(*this); // own device model: the class is not re-entrant (reference MSV_HMM.cpp:59-64)
+                replica.set_device(devices[part]);
+                const auto first = bounds[part], last = bounds[part + 1];
+                if (first == last) return;
+                // offsets of the slice, rebased to its first residue
+                auto offsets = std::vector<uint64_t>(database.offsets.begin() + static_cast<std::ptrdiff_t>(first),
+                                                     database.offsets.begin() + static_cast<std::ptrdiff_t>(last) + 1);
+                const auto base = offsets.front();
+                for (auto& o : offsets) o -= base;
+                const auto status = msv_cuda_score_batch(replica.on_device(), database.residues.data() + base, offsets.data(),
+                                                         last - first, scores.data() + first);
+                if (status != MSV_OK) failures[part] = msv_cuda_last_error();
+            } catch (const std::exception& e) {
+                failures[part] = e.what();
+            }
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (const auto& f : failures)
+        if (!f.empty()) throw std::runtime_error("MSV_HMM::parallel_run_on_sequences: " + f);
     return scores;
 }
 

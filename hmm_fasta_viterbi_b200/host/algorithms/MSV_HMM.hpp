@@ -47,6 +47,11 @@ class MSV_HMM {
     std::vector<Log_score> parallel_run_on_sequences(const Protein_sequences& sequences);
     std::vector<Log_score> parallel_run_on_sequences(const Packed_sequences& database);
 
+    // The same over several GPUs of one box from ONE process: the database is cut into contiguous slices of equal
+    // cell count, one host thread and one device model per GPU; scores land directly in the result vector, so there
+    // is no collective.  (The one-process-per-GPU variant with an NCCL gather is hmm_fasta_viterbi_b200/sharded.py.)
+    std::vector<Log_score> parallel_run_on_sequences(const Packed_sequences& database, const std::vector<int>& devices);
+
     size_t length() const { return model_length; } // LENG + 1
     int device() const { return device_index; }
     void set_device(int device); // drops the device model; it is re-created lazily on the chosen GPU

@@ -128,4 +128,12 @@ int msvh_msv_parallel_run_on_packed(void* m, void* packed, float* scores) {
     });
 }
 
+int msvh_msv_parallel_run_on_packed_devices(void* m, void* packed, const int* devices, int n_devices, float* scores) {
+    return guarded([&] {
+        const auto got = static_cast<MSV_HMM*>(m)->parallel_run_on_sequences(*static_cast<Packed_sequences*>(packed),
+                                                                             std::vector<int>(devices, devices + n_devices));
+        if (!got.empty()) std::memcpy(scores, got.data(), got.size() * sizeof(float));
+    });
+}
+
 } // extern "C"

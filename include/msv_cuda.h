@@ -17,6 +17,8 @@
  *     (sequence q = residues[offsets[q] .. offsets[q+1]) ).
  *   - scores are fp32 and bit-identical to MSV_HMM::run_on_sequence (reference MSV_HMM.cpp:74-113).
  *   - there is no CPU fallback: without a CUDA device every msv_cuda_* call fails with MSV_ERR_NO_DEVICE.
+ *   - thread safety: calls that share a msv_model or a msv_db must be serialised by the caller (the reference's
+ *     MSV_HMM is not re-entrant either, MSV_HMM.cpp:59-64); distinct handles may be used from distinct threads.
  */
 #ifndef MSV_CUDA_H
 #define MSV_CUDA_H
@@ -106,6 +108,20 @@ int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host);
 int msv_cuda_score_batch(msv_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host);
 /* one sequence, synchronous: the body of MSV_HMM::parallel_run_on_sequence (reference MSV_HMM.cpp:269-430). */
 int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * MSV filter statistics (the step that follows the scan in HMMER3's pipeline; the reference parses the model's
+ * "STATS LOCAL MSV mu lambda" line, Profile_HMM.cpp:82-85, but never uses it).  For every sequence of `db`, from the
+ * raw scores (nats) left on the device by msv_cuda_db_score_device:
+ *     null1(L) = L * log(L / (L + 1)) + log(1 / (L + 1))            length model of the null hypothesis
+ *     bits     = (score - null1(L)) / ln 2
+ *     P        = 1 - exp(-exp(-lambda * (bits - mu)))               Gumbel survival; -expm1 form for tiny values
+ * evaluated in fp64 on the device and stored as fp32.  Either output pointer may be NULL.  Asynchronous on
+ * `cuda_stream`.  Unlike the scan this is ordinary floating point: results agree with an fp64 host evaluation to
+ * 1e-6 relative (tests/test_gpu_parity.py), not bit for bit.
+ * ------------------------------------------------------------------------------------------------------------- */
+int msv_cuda_db_filter_device(msv_db* db, const float* scores_device, float mu, float lambda, float* bits_device,
+                              float* pvalues_device, void* cuda_stream);
 
 /* kernel launches issued by this library on the calling thread since the last reset (for bench.py's gpu_launches) */
 uint64_t msv_cuda_launch_count(int reset);

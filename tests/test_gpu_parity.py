@@ -205,6 +205,42 @@ def test_short_model_large_database_uses_eight_lanes_per_sequence(oracle):
     assert (ubits(model.score_batch(codes, offsets)) == ubits(got)).all()
 
 
+def test_single_process_multi_device_driver(oracle):
+    """MSV_HMM::parallel_run_on_sequences(db, devices): two slices scored concurrently (here both on GPU 0 when the box
+    has one GPU) equal the single-call result."""
+    model = msv.MSV_HMM(msv.Profile_HMM(hmm_path("900.hmm")))
+    packed = msv.Packed_sequences.synthetic_swissprot_like(20_000, 9)
+    one = model.parallel_run_on_sequences(packed)
+    devices = [0, 1] if _cabi.device_count() > 1 else [0, 0]
+    two = model.parallel_run_on_sequences(packed, devices=devices + [0])
+    assert (ubits(one) == ubits(two)).all()
+
+
+def test_filter_statistics_bits_and_pvalues(oracle):
+    """Bit score and Gumbel P-value of the MSV filter (floating point, tolerance 1e-6 relative vs fp64 numpy)."""
+    import torch
+
+    prof = msv.Profile_HMM(hmm_path("500.hmm"))
+    model, table, tr3 = device_model(oracle, "500.hmm")
+    packed = msv.Packed_sequences.synthetic_swissprot_like(5000, 55)
+    db = msv.Database(packed.residues, packed.offsets)
+    scores = torch.empty(len(packed), dtype=torch.float32, device="cuda")
+    bits_d, p_d = torch.empty_like(scores), torch.empty_like(scores)
+    stream = torch.cuda.current_stream().cuda_stream
+    db.score_device(model, scores, stream)
+    db.filter_device(scores, prof.stats_local_msv_mu, prof.stats_local_msv_lambda, bits_d, p_d, stream)
+    torch.cuda.synchronize()
+    raw = scores.cpu().numpy().astype(np.float64)
+    L = np.diff(packed.offsets.astype(np.int64)).astype(np.float64)
+    null1 = L * np.log(L / (L + 1.0)) + np.log(1.0 / (L + 1.0))
+    bits = (raw - null1) / np.log(2.0)
+    ey = -np.exp(-float(prof.stats_local_msv_lambda) * (bits - float(prof.stats_local_msv_mu)))
+    pv = np.where(np.abs(ey) < 5e-9, -ey, 1.0 - np.exp(ey))
+    np.testing.assert_allclose(bits_d.cpu().numpy(), bits, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(p_d.cpu().numpy(), pv, rtol=1e-5, atol=1e-12)
+    assert 0.0 <= pv.min() and pv.max() <= 1.0
+
+
 # ---- edge cases --------------------------------------------------------------------------------------------------
 def test_edge_cases(oracle):
     model, table, tr3 = device_model(oracle, "1400.hmm")
