@@ -58,6 +58,7 @@ struct Geometry {
     int G, K, KT, threads;
     Scan_kernel fn;         // general transitions
     Scan_kernel fn_cj_same; // tr_E_C == tr_E_J bitwise (C is J); same as fn for the generic family
+    int variant = 0;        // reserved for tuning variants (none at present)
     size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET) * (K - std::max(KT, 0)) * G * sizeof(float); }
 };
 
@@ -100,9 +101,9 @@ const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(M
                                  quad_entry<24, 16>(), quad_entry<28, 16>(), quad_entry<32, 16>(), quad_entry<36, 16>(),
                                  quad_entry<40, 24>(), quad_entry<44, 24>()};
 
-const Geometry* find_geometry(int G, int K, int KT, int threads = 0) {
+const Geometry* find_geometry(int G, int K, int KT, int threads = 0, int variant = 0) {
     for (const auto& g : g_geometries)
-        if (g.G == G && g.K == K && g.KT == KT && (threads == 0 || g.threads == threads)) return &g;
+        if (g.G == G && g.K == K && g.KT == KT && (threads == 0 || g.threads == threads) && g.variant == variant) return &g;
     return nullptr;
 }
 
@@ -111,15 +112,15 @@ int round_up4(size_t v) { return static_cast<int>((v + 3) / 4 * 4); }
 // Default: one warp per sequence with the shared-memory + tensor-memory split (that kernel needs the last column of
 // lane 31 to be padding, hence 32*K > columns).  The generic family (8/16/32 lanes per sequence, shared memory only) is
 // kept for comparison and for devices/contexts where TMEM is unavailable.
-// MSV_CUDA_GEOMETRY="G,K[,KT[,threads]]" overrides the choice (tuning aid; without KT the generic kernel is selected).
+// MSV_CUDA_GEOMETRY="G,K[,KT[,threads[,variant]]]" overrides the choice (tuning aid; without KT the generic kernel is selected).
 const Geometry* choose_geometry(size_t columns) {
     if (const char* env = std::getenv("MSV_CUDA_GEOMETRY")) {
-        int G = 0, K = 0, KT = -1, T = 0;
-        const int got = std::sscanf(env, "%d,%d,%d,%d", &G, &K, &KT, &T);
+        int G = 0, K = 0, KT = -1, T = 0, V = 0;
+        const int got = std::sscanf(env, "%d,%d,%d,%d,%d", &G, &K, &KT, &T, &V);
         if (got == 2 && static_cast<size_t>(G) * K > columns)
             if (const Geometry* g = find_geometry(G, K, -1)) return g;
         if (got >= 3 && static_cast<size_t>(G) * K > columns)
-            if (const Geometry* g = find_geometry(G, K, KT, T)) return g;
+            if (const Geometry* g = find_geometry(G, K, KT, T, V)) return g;
     }
     // Measured on B200 over the 24 fixture models (profiles/r01/sweep_models_v2.jsonl, sweep_kt_v2.jsonl): the
     // warp-per-sequence kernel with the shared-memory/tensor-memory split wins at every model length, with 16 tensor-memory
@@ -240,7 +241,8 @@ int db_check_offsets(const uint8_t* residues, const uint64_t* offsets, size_t n,
     }
     const uint64_t total = n ? offsets[n] : 0;
     if (total > 0 && !residues) return fail(MSV_ERR_INVALID_ARGUMENT, "residues is NULL");
-    if (longest >= (1ull << 31)) return fail(MSV_ERR_INVALID_ARGUMENT, "sequence longer than 2^31-1 residues");
+    if (longest >= (1ull << 27)) // the per-length transition table would exceed 1 GB; no protein comes close
+        return fail(MSV_ERR_INVALID_ARGUMENT, "sequence of %llu residues exceeds the supported 2^27-1", static_cast<unsigned long long>(longest));
     *total_out = total;
     *longest_out = longest;
     return MSV_OK;
@@ -313,6 +315,10 @@ int db_prepare_range(msv_db* db, size_t first, size_t count, uint64_t residue_be
         msv::db_validate_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(db->d_residues) + word_begin, words,
                                                              residue_end - word_begin * 16, word_begin * 16, db->d_first_bad);
         ++g_launches;
+    }
+    if (count == 1) { // single-sequence calls: the order is trivially {0}
+        MSV_CUDA_TRY(cudaMemsetAsync(db->d_order + first, 0, sizeof(uint32_t), stream));
+        return MSV_OK;
     }
     uint32_t shift = 0;
     while ((longest >> shift) >= kBuckets) ++shift;
