@@ -180,6 +180,7 @@ struct msv_db {
     unsigned int* d_queue = nullptr;
     unsigned long long* d_first_bad = nullptr;
     std::vector<float2> h_length_tr; // host copy, extended lazily
+    std::vector<uint32_t> h_lengths; // sequence lengths, kept on the host only for small databases (launch planning)
     // pipelined upload (msv_cuda_score_batch): copy engine and scan overlap
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     cudaEvent_t stage_copied[kMaxChunks] = {};
@@ -347,6 +348,14 @@ int db_read_validation(msv_db* db, const uint8_t* residues, cudaStream_t stream)
     return MSV_OK;
 }
 
+// Small databases keep their lengths on the host: the launch planner needs them to balance few long sequences.
+void db_keep_lengths(msv_db* db, const uint64_t* offsets, size_t n) {
+    db->h_lengths.clear();
+    if (n == 0 || n > 65536) return;
+    db->h_lengths.resize(n);
+    for (size_t q = 0; q < n; ++q) db->h_lengths[q] = static_cast<uint32_t>(offsets[q + 1] - offsets[q]);
+}
+
 // (Re)fill `db` from host buffers in one piece: upload, validate, per-length transitions, longest-first order.
 // Returns after the validation result has been read back (one small synchronisation).
 int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n, cudaStream_t stream) {
@@ -363,34 +372,103 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
     db->n = n;
     db->total = total;
     db->longest = longest;
+    db_keep_lengths(db, offsets, n);
     if (n == 0) return MSV_OK;
     if (int rc = db_prepare_range(db, 0, n, 0, total, longest, stream)) return rc;
     return db_read_validation(db, residues, stream);
 }
 
-// Which plan scans `count` sequences holding `residues` residues, the longest of them `longest`:
-//   * the four-warp plan when there are too few sequences to fill the warp slots of the bulk plan (the makespan would
-//     be one long sequence on a sixteenth of an SM), or when the model has no bulk plan;
-//   * the eight-lane plan for short models when the average slot still gets about as many rows as the longest
-//     sequence has (it has four times more slots than the warp plan; with less work per slot the longest sequence
-//     alone sets the makespan -- measured break-even on B200, profiles/r01/sweep_generic_v3.jsonl);
-//   * else one warp per sequence.
-const msv_model::Plan& pick_plan(const msv_model* model, size_t count, uint64_t residues, uint64_t longest) {
-    if (!model->bulk.geo) return model->quad;
-    if (model->forced) return model->bulk;
-    const auto slots = [&](const msv_model::Plan& plan) {
-        return static_cast<uint64_t>(model->sm_count) * (plan.geo->threads / plan.geo->G);
+// ---- launch planning ------------------------------------------------------------------------------------------------
+// With millions of sequences every plan is balanced and the choice is static.  With few (long) sequences the scan is a
+// scheduling problem: sequences are serial, a slot (warp / four warps) scans one at a time, so the makespan is set by
+// the longest-processing-time-first assignment of whole sequences to slots -- and fewer, faster slots can win.
+// The planner simulates that assignment for each candidate (plan, slots per SM) and weighs it with the measured
+// throughput of that kernel at that occupancy (B200, profiles/r01/occupancy_curve_*.jsonl, relative to the warp kernel
+// at full occupancy).
+struct Launch_plan {
+    const msv_model::Plan* plan;
+    size_t slots_per_cta;
+};
+
+// throughput of the warp kernel at `fraction` of its maximum warps per SM (measured: 25 % -> 0.51, 50 % -> 0.885, 75 % -> 0.98)
+double warp_occupancy_factor(double fraction) {
+    static const double x[] = {0.0, 0.25, 0.5, 0.75, 1.0}, y[] = {0.0, 0.51, 0.885, 0.98, 1.0};
+    for (int i = 1; i < 5; ++i)
+        if (fraction <= x[i]) return y[i - 1] + (y[i] - y[i - 1]) * (fraction - x[i - 1]) / (x[i] - x[i - 1]);
+    return 1.0;
+}
+
+// throughput of the four-warp kernel with `groups` of `max_groups` per SM (measured at K = 20: 3.4 ... 7.0 TCUPS vs 9.2)
+double quad_occupancy_factor(size_t groups, size_t max_groups) {
+    static const double x[] = {0.0, 1.0 / 6, 2.0 / 6, 3.0 / 6, 4.0 / 6, 5.0 / 6, 1.0}, y[] = {0.0, 0.37, 0.61, 0.685, 0.724, 0.745, 0.758};
+    const double fraction = static_cast<double>(groups) / static_cast<double>(max_groups);
+    for (int i = 1; i < 7; ++i)
+        if (fraction <= x[i] + 1e-9) return y[i - 1] + (y[i] - y[i - 1]) * (fraction - x[i - 1]) / (x[i] - x[i - 1]);
+    return y[6];
+}
+
+// rows of the busiest slot when `lengths` (sorted, longest first) are handed to `slots` workers greedily
+uint64_t lpt_makespan(const std::vector<uint32_t>& lengths, size_t slots) {
+    if (lengths.empty()) return 0;
+    if (slots >= lengths.size()) return lengths.front();
+    std::vector<uint64_t> heap(slots, 0); // min-heap of slot loads
+    for (const uint32_t len : lengths) {
+        std::pop_heap(heap.begin(), heap.end(), std::greater<uint64_t>());
+        heap.back() += len;
+        std::push_heap(heap.begin(), heap.end(), std::greater<uint64_t>());
+    }
+    return *std::max_element(heap.begin(), heap.end());
+}
+
+Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, size_t count, uint64_t residues) {
+    const auto max_slots = [](const msv_model::Plan& plan) { return static_cast<size_t>(plan.geo->threads / plan.geo->G); };
+    if (!model->bulk.geo) return {&model->quad, max_slots(model->quad)};
+    if (model->forced) return {&model->bulk, max_slots(model->bulk)};
+    const size_t sms = static_cast<size_t>(model->sm_count);
+    const size_t bulk_slots = sms * max_slots(model->bulk);
+
+    // plenty of sequences: static choice (the eight-lane plan needs about as many rows per slot as the longest sequence
+    // has, because it has four times more slots -- measured break-even, profiles/r01/sweep_generic_v3.jsonl)
+    // (planning costs ~1 ms of host time at most; it pays only when the sequences are long enough for balance to matter)
+    const bool few = count < 4 * bulk_slots && residues >= 1000 * static_cast<uint64_t>(count) && db->h_lengths.size() == db->n &&
+                     model->bulk.geo->G == 32;
+    if (!few) {
+        if (model->octet.geo && 4 * (residues / (sms * max_slots(model->octet))) >= 3 * std::max<uint64_t>(db->longest, 1))
+            return {&model->octet, max_slots(model->octet)};
+        if (model->quad.geo && count < 2 * bulk_slots) return {&model->quad, max_slots(model->quad)};
+        return {&model->bulk, max_slots(model->bulk)};
+    }
+
+    // few sequences: pick (plan, slots per SM) by simulated makespan x measured per-slot speed
+    std::vector<uint32_t> lengths(db->h_lengths.begin() + static_cast<std::ptrdiff_t>(first),
+                                  db->h_lengths.begin() + static_cast<std::ptrdiff_t>(first + count));
+    std::sort(lengths.begin(), lengths.end(), std::greater<uint32_t>());
+    Launch_plan best{&model->bulk, max_slots(model->bulk)};
+    double best_cost = std::numeric_limits<double>::infinity();
+    const auto consider = [&](const msv_model::Plan& plan, size_t slots_per_sm, double relative_throughput) {
+        const size_t ctas = std::min(sms, (count + slots_per_sm - 1) / slots_per_sm);
+        const double cost = static_cast<double>(lpt_makespan(lengths, ctas * slots_per_sm)) * static_cast<double>(slots_per_sm) /
+                            relative_throughput;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = {&plan, slots_per_sm};
+        }
     };
-    if (model->quad.geo && count < 2 * slots(model->bulk)) return model->quad;
-    if (model->octet.geo && 4 * (residues / slots(model->octet)) >= 3 * std::max<uint64_t>(longest, 1)) return model->octet;
-    return model->bulk;
+    const size_t max_warps = max_slots(model->bulk);
+    for (size_t warps = 4; warps <= max_warps; warps += 4) // whole warps per scheduler: 4 SM sub-partitions
+        consider(model->bulk, warps, warp_occupancy_factor(static_cast<double>(warps) / static_cast<double>(max_warps)));
+    if (model->quad.geo)
+        for (size_t groups = 1; groups <= max_slots(model->quad); ++groups)
+            consider(model->quad, groups, quad_occupancy_factor(groups, max_slots(model->quad)));
+    return best;
 }
 
 // One launch of the scan over sequences [first, first+count) of `db`; scores go to d_scores[first ..).
 int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64_t residues, int queue_slot, float* d_scores,
                 cudaStream_t stream) {
     if (count == 0) return MSV_OK;
-    const msv_model::Plan& plan = pick_plan(model, count, residues, db->longest);
+    const Launch_plan chosen = plan_launch(model, db, first, count, residues);
+    const msv_model::Plan& plan = *chosen.plan;
     const Geometry* geo = plan.geo;
     msv::Scan_params p{};
     p.table = plan.d_table;
@@ -410,15 +488,11 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue + queue_slot, 0, sizeof(unsigned int), stream));
     // persistent CTAs, at most one per SM; a "slot" scans one sequence at a time (lane group, warp or four warps)
     const size_t threads_per_slot = static_cast<size_t>(geo->G);
-    const size_t slots_per_cta = geo->threads / threads_per_slot;
-    size_t ctas, slots;
-    if (geo->G == 128) { // spread few sequences over as many SMs as possible
-        ctas = std::min<size_t>(model->sm_count, count);
-        slots = std::min<size_t>(slots_per_cta, (count + ctas - 1) / ctas);
-    } else {
-        ctas = std::max<size_t>(1, std::min<size_t>(model->sm_count, (count + slots_per_cta - 1) / slots_per_cta));
-        slots = ctas == 1 ? std::min<size_t>(slots_per_cta, count) : slots_per_cta;
-    }
+    size_t slots = std::min<size_t>(chosen.slots_per_cta, geo->threads / threads_per_slot);
+    if (const char* env = std::getenv(geo->G == 128 ? "MSV_CUDA_QUAD_GROUPS" : "MSV_CUDA_BULK_SLOTS")) // tuning aid
+        slots = std::min<size_t>(geo->threads / threads_per_slot, std::max(1, std::atoi(env)));
+    const size_t ctas = std::max<size_t>(1, std::min<size_t>(model->sm_count, (count + slots - 1) / slots));
+    if (ctas == 1) slots = std::min(slots, count); // do not launch slots that would find the queue empty
     const int threads = static_cast<int>(std::max<size_t>(32, (slots * threads_per_slot + 31) / 32 * 32));
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
     (cj_same ? geo->fn_cj_same : geo->fn)<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
@@ -446,6 +520,7 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
     db->n = n;
     db->total = total;
     db->longest = longest;
+    db_keep_lengths(db, offsets, n);
     if (n == 0) return MSV_OK;
 
     // Stages grow geometrically: the first one is small so that the scan starts almost immediately, and every later
@@ -454,8 +529,10 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
     int stages = 0;
     bounds[0] = 0;
     {
+        // few sequences: one stage, so that the launch planner can balance them all at once (the upload is short anyway)
+        const size_t warp_slots = static_cast<size_t>(model->sm_count) * 16;
         uint64_t stage_bytes = 2ull << 20, cut = 0;
-        while (stages < kMaxChunks - 1 && cut + stage_bytes + (stage_bytes >> 1) < total) {
+        while (n >= 4 * warp_slots && stages < kMaxChunks - 1 && cut + stage_bytes + (stage_bytes >> 1) < total) {
             cut += stage_bytes;
             size_t q = static_cast<size_t>(std::lower_bound(offsets, offsets + n + 1, cut) - offsets);
             q = std::min(q, n);
