@@ -1,27 +1,31 @@
 // msv_kernels.cuh -- hand-written sm_100a kernels of the MSV scan.
 //
-// What the kernel computes (per sequence, fp32, only `+` and `max`): the recurrence of the reference's
+// What the kernels compute (per sequence, fp32, only `+` and `max`): the recurrence of the reference's
 // MSV_HMM::run_on_sequence (reference algorithms/MSV_HMM.cpp:96-112), i.e. the fusion of its six OpenCL kernels
 // (algorithms/MSV_kernels.cl:1-65: init_dp, init_N_B, M_states_handler, copy_M, reduction_step, E_J_C_N_B_handler)
 // and of the host loop that launches them 13 times per residue (MSV_HMM.cpp:382-423) into ONE launch per database.
 //
-// How (B200 design, not a translation):
-//   * a GROUP of G lanes (G = 8, 16 or 32) owns one sequence; a warp therefore scans 32/G sequences at once.
-//     Lane g of the group keeps K consecutive model columns  g*K+1 .. g*K+K  of the DP row in REGISTERS (m[K]).
-//     The row never touches memory.
+// Three kernel families share one design (B200-first, not a translation):
+//   msv_scan_warp_kernel   one warp per sequence; emissions from shared memory AND tensor memory   -- the hot kernel
+//   msv_scan_kernel        G = 8/16/32 lanes per sequence, 32/G sequences per warp                  -- short models
+//   msv_scan_quad_kernel   four warps per sequence; table distributed over shared + tensor memory   -- few/long sequences,
+//                                                                                                     models > 2815 columns
+// Common to all:
+//   * the lanes that own a sequence keep its DP row in REGISTERS (m[K]: K consecutive model columns per lane); the row
+//     never touches memory;
 //   * the k-1 dependency is satisfied inside a lane by updating m[] from the highest column downwards (every cell
-//     reads the not-yet-overwritten left neighbour), and across lanes by ONE __shfl_up_sync per row.
-//   * E = max_k M is a per-lane FMNMX3 tree followed by a group max (CREDUX.MAX.F32 when G == 32, xor-shuffles
-//     otherwise); the special states N/J/C/B are carried redundantly by every lane of the group.
-//   * the emission table ([residue][column]) is staged ONCE per CTA into shared memory by bulk-async (TMA) copies
-//     completing on an mbarrier; its layout [residue][quad][lane][4] makes every access a conflict-free LDS.128.
-//     Columns beyond the model are padded with -inf, so they never win a max.
-//   * CTAs are persistent (one per SM); groups pull sequences longest-first from a global atomic queue, so a warp
-//     is never idle while work remains and long sequences start first.
+//     reads the not-yet-overwritten left neighbour), and across lanes by ONE shuffle per row; the shuffle ROTATES, and
+//     because the last column of the last lane is -inf padding, lane 0 receives the -inf of the dummy column M0 for free;
+//   * E = max_k M is a per-lane FMNMX3 chain followed by a cross-lane max (CREDUX.MAX.F32 for whole warps, xor-shuffles
+//     for lane groups); the special states N/J/B are carried redundantly by every lane; C is J when tr_E_C == tr_E_J;
+//   * the emission table ([residue][column]) is staged ONCE per CTA: the shared-memory part by bulk-async (TMA) copies
+//     completing on an mbarrier, laid out [residue][quad][lane][4] so that every access is a conflict-free LDS.128; the
+//     tensor-memory part by tcgen05.st, read back with tcgen05.ld; columns beyond the model are -inf;
+//   * CTAs are persistent (one per SM); slots pull sequences longest-first from a global atomic queue;
 //   * residues stream from HBM as aligned 32-bit words (4 residues), prefetched one word ahead.
 // Exactness: every cell performs the same fp32 add on the same operands as the reference; max is exact and
 // order-independent for the non-NaN values that can occur (-inf and finite numbers only), so scores are
-// bit-identical to the reference for any summation order of the E reduction.
+// bit-identical to the reference for any order of the E reduction.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -38,13 +42,12 @@ struct Scan_params {
     const uint8_t* residues;  // concatenated residue codes, padded by kResiduePadBytes
     const uint64_t* offsets;  // n + 1
     const uint32_t* order;    // n sequence indices, longest first
-    const float2* length_tr;  // (tr_loop, tr_move): indexed by length, or by sequence when tr_by_sequence != 0
+    const float2* length_tr;  // (tr_loop, tr_move) indexed by sequence length (host libm, reference MSV_HMM.cpp:59-64)
     float* scores;            // n, original order
     unsigned int* queue_head; // work queue cursor, zero before launch
     const unsigned long long* first_bad; // position of the first invalid residue code found by db_validate_kernel, or ~0
     uint32_t n;
     uint32_t table_bytes;
-    uint32_t tr_by_sequence;
     float tr_B_Mk, tr_E_C, tr_E_J;
 };
 
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
             idx = __ldg(p.order + ticket);
             const uint64_t begin = __ldg(p.offsets + idx);
             const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
-            const float2 tr = __ldg(p.length_tr + (p.tr_by_sequence ? idx : len));
+            const float2 tr = __ldg(p.length_tr + len);
             loop = tr.x;
             move = tr.y;
 #pragma unroll
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         const uint32_t idx = __ldg(p.order + ticket);
         const uint64_t begin = __ldg(p.offsets + idx);
         const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
-        const float2 tr = __ldg(p.length_tr + (p.tr_by_sequence ? idx : len));
+        const float2 tr = __ldg(p.length_tr + len);
         const float loop = tr.x, move = tr.y;
 
         float m[K];
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_quad_kernel(const Scan_pa
         const uint32_t idx = __ldg(p.order + ticket);
         const uint64_t begin = __ldg(p.offsets + idx);
         const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
-        const float2 tr = __ldg(p.length_tr + (p.tr_by_sequence ? idx : len));
+        const float2 tr = __ldg(p.length_tr + len);
         const float loop = tr.x, move = tr.y;
 
         float m[K];
