@@ -199,6 +199,7 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device; the MSV scan has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     model_path = os.path.join(REPO, "fixtures", "profile_HMMs", args.model)
