@@ -132,10 +132,11 @@ const Geometry* choose_geometry(size_t columns) {
 }
 
 // Eight lanes per sequence (four sequences per warp) pays off for short models: measured on B200
-// (profiles/r01/sweep_generic_v3.jsonl) it beats the warp plan for LENG 200-447 when there are enough sequences.
+// (profiles/r01/sweep_generic_v3.jsonl) it beats the warp plan for LENG 200-447 when there are enough sequences to
+// balance its four times more slots (plan_launch checks that per launch).
 const Geometry* choose_octet_geometry(size_t columns) {
     const int K = std::max(4, round_up4((columns + 1 + 7) / 8)); // 8*K > columns
-    return (columns >= 150 && K <= 56) ? find_geometry(8, K, -1) : nullptr;
+    return (columns >= 64 && K <= 56) ? find_geometry(8, K, -1) : nullptr;
 }
 
 // Four warps per sequence: the plan for few/long sequences and for models beyond one warp's registers.

@@ -137,6 +137,17 @@ def test_run_on_sequence_matches_golden(golden_scores, golden_readers, name):
         assert [bits(model.run_on_sequence(s)) for s in seqs[key]] == want
 
 
+@pytest.mark.parametrize("prog", ["test_hmm_parsing", "test_fasta_parsing"])
+def test_reference_reader_tests_pass_unchanged(prog):
+    """The reference's own reader tests (data_readers/test_hmm_parsing.cpp, test_fasta_parsing.cpp), compiled unchanged
+    against this implementation's readers with asserts enabled (tools/build_reference_programs.sh)."""
+    exe = os.path.join(REPO, "build", "data_readers", prog)
+    if not os.path.exists(exe):
+        pytest.skip("build/ not populated (needs /root/reference at build time)")
+    run = subprocess.run([exe], cwd=os.path.dirname(exe), capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+
+
 def test_partition_by_cells():
     rng = np.random.default_rng(3)
     lens = rng.integers(0, 500, size=1000)
