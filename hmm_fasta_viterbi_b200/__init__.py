@@ -11,7 +11,7 @@ fallback for the GPU path.
 """
 from . import _cabi
 from ._cabi import Database, Model, MsvCudaError
-from .host import FASTA_protein_sequences, MSV_HMM, Packed_sequences, Profile_HMM
+from .host import Device_database, FASTA_protein_sequences, MSV_HMM, Packed_sequences, Profile_HMM
 
-__all__ = ["Database", "Model", "MsvCudaError", "FASTA_protein_sequences", "MSV_HMM", "Packed_sequences", "Profile_HMM",
+__all__ = ["Database", "Device_database", "Model", "MsvCudaError", "FASTA_protein_sequences", "MSV_HMM", "Packed_sequences", "Profile_HMM",
            "_cabi"]

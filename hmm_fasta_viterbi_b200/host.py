@@ -69,6 +69,10 @@ lib.msvh_msv_length.argtypes = [_vp]
 lib.msvh_msv_run_on_sequence.argtypes = [_vp, C.c_char_p, C.POINTER(C.c_float)]
 lib.msvh_msv_parallel_run_on_sequence.argtypes = [_vp, C.c_char_p, C.c_int, C.POINTER(C.c_float)]
 lib.msvh_msv_parallel_run_on_packed.argtypes = [_vp, _vp, _f32]
+lib.msvh_device_database_create.restype = _vp
+lib.msvh_device_database_create.argtypes = [_vp, C.c_int]
+lib.msvh_device_database_free.argtypes = [_vp]
+lib.msvh_msv_parallel_run_on_device_database.argtypes = [_vp, _vp, _f32]
 lib.msvh_msv_parallel_run_on_packed_devices.argtypes = [_vp, _vp, C.POINTER(C.c_int), C.c_int, _f32]
 
 
@@ -179,6 +183,24 @@ class Packed_sequences:
             self._h = None
 
 
+class Device_database:
+    """A Packed_sequences uploaded once and kept in HBM (host/algorithms/MSV_HMM.hpp), scanned by any number of models."""
+
+    def __init__(self, packed: Packed_sequences, device: int = 0) -> None:
+        self._h = lib.msvh_device_database_create(packed._h, device)
+        if not self._h:
+            _raise(-1)
+        self._n = len(packed)
+
+    def __len__(self) -> int:
+        return self._n
+
+    def __del__(self) -> None:
+        if getattr(self, "_h", None):
+            lib.msvh_device_database_free(self._h)
+            self._h = None
+
+
 class MSV_HMM:
     """algorithms/MSV_HMM.hpp:17-24 plus the batch entry point this implementation adds."""
 
@@ -207,6 +229,11 @@ class MSV_HMM:
         if isinstance(database, FASTA_protein_sequences):
             database = Packed_sequences.from_fasta(database)
         out = np.empty(max(len(database), 1), np.float32)
+        if isinstance(database, Device_database):
+            status = lib.msvh_msv_parallel_run_on_device_database(self._h, database._h, out)
+            if status:
+                _raise(status)
+            return out[: len(database)]
         if devices:
             arr = (C.c_int * len(devices))(*devices)
             status = lib.msvh_msv_parallel_run_on_packed_devices(self._h, database._h, arr, len(devices), out)

@@ -16,6 +16,14 @@ namespace {
 
 } // namespace
 
+Device_database::Device_database(const Packed_sequences& database, int device)
+    : sequences(database.size()), residues(database.total_residues()), device_index(device) {
+    msv_db* raw = nullptr;
+    const auto status = msv_cuda_db_create(device, database.residues.data(), database.offsets.data(), database.size(), &raw);
+    if (status != MSV_OK) throw_last_error("Device_database: cannot upload the database", status);
+    resident = std::shared_ptr<msv_db>(raw, [](msv_db* db) { msv_cuda_db_destroy(db); });
+}
+
 // Model preparation.  All fp32 expressions (log-odds table, B->M_k, E->C, E->J) are evaluated by the shared host
 // helpers of the C ABI so that the C++ class and every other binding produce the same bits as the reference
 // constructor (reference MSV_HMM.cpp:35-53).
@@ -95,6 +103,14 @@ std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Packed_sequences
     auto scores = std::vector<Log_score>(database.size());
     const auto status = msv_cuda_score_batch(on_device(), database.residues.data(), database.offsets.data(), database.size(),
                                              scores.data());
+    if (status != MSV_OK) throw_last_error("MSV_HMM::parallel_run_on_sequences", status);
+    return scores;
+}
+
+std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Device_database& database) {
+    if (database.device() != device_index) set_device(database.device());
+    auto scores = std::vector<Log_score>(database.size());
+    const auto status = msv_cuda_db_score(on_device(), database.handle(), scores.data());
     if (status != MSV_OK) throw_last_error("MSV_HMM::parallel_run_on_sequences", status);
     return scores;
 }

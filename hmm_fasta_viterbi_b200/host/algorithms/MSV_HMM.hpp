@@ -32,6 +32,26 @@ template <int N> using Log_scores_arrays_vector = std::vector<Log_scores_array<N
 using Kernels_source_code = std::string; // kept for source compatibility; kernels are compiled in, nothing is read at run time
 
 struct msv_model; // opaque device model of the C ABI
+struct msv_db;    // opaque device-resident database of the C ABI
+
+// A sequence database uploaded once and kept in HBM (validated, bucketed longest-first), to be scanned by any number of
+// models without touching the host again -- the natural shape of "all models against one database"
+// (reference benchmark_MSV.cpp:26-41 loops 24 models over the same sequences).  Cheap to copy (shared handle).
+class Device_database {
+  public:
+    explicit Device_database(const Packed_sequences& database, int device = 0);
+
+    size_t size() const { return sequences; }
+    uint64_t total_residues() const { return residues; }
+    int device() const { return device_index; }
+    msv_db* handle() const { return resident.get(); }
+
+  private:
+    std::shared_ptr<msv_db> resident;
+    size_t sequences = 0;
+    uint64_t residues = 0;
+    int device_index = 0;
+};
 
 class MSV_HMM {
   public:
@@ -46,6 +66,9 @@ class MSV_HMM {
     // GPU, whole database in one launch; scores come back in input order.
     std::vector<Log_score> parallel_run_on_sequences(const Protein_sequences& sequences);
     std::vector<Log_score> parallel_run_on_sequences(const Packed_sequences& database);
+
+    // GPU, database already resident in HBM (Device_database): only the scores cross PCIe.
+    std::vector<Log_score> parallel_run_on_sequences(const Device_database& database);
 
     // The same over several GPUs of one box from ONE process: the database is cut into contiguous slices of equal
     // cell count, one host thread and one device model per GPU; scores land directly in the result vector, so there

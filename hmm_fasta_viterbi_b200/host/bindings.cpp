@@ -128,6 +128,19 @@ int msvh_msv_parallel_run_on_packed(void* m, void* packed, float* scores) {
     });
 }
 
+void* msvh_device_database_create(void* packed, int device) {
+    Device_database* d = nullptr;
+    guarded([&] { d = new Device_database(*static_cast<Packed_sequences*>(packed), device); });
+    return d;
+}
+void msvh_device_database_free(void* d) { delete static_cast<Device_database*>(d); }
+int msvh_msv_parallel_run_on_device_database(void* m, void* d, float* scores) {
+    return guarded([&] {
+        const auto got = static_cast<MSV_HMM*>(m)->parallel_run_on_sequences(*static_cast<Device_database*>(d));
+        if (!got.empty()) std::memcpy(scores, got.data(), got.size() * sizeof(float));
+    });
+}
+
 int msvh_msv_parallel_run_on_packed_devices(void* m, void* packed, const int* devices, int n_devices, float* scores) {
     return guarded([&] {
         const auto got = static_cast<MSV_HMM*>(m)->parallel_run_on_sequences(*static_cast<Packed_sequences*>(packed),

@@ -205,6 +205,21 @@ def test_short_model_large_database_uses_eight_lanes_per_sequence(oracle):
     assert (ubits(model.score_batch(codes, offsets)) == ubits(got)).all()
 
 
+def test_resident_database_scanned_by_many_models(oracle):
+    """Device_database: one upload, every fixture model scans it (the benchmark_MSV.cpp pattern); bits equal the
+    host-buffer path and the oracle."""
+    packed = msv.Packed_sequences.synthetic_swissprot_like(3000, 123)
+    resident = msv.Device_database(packed)
+    for name in ("100.hmm", "800.hmm", "1400.hmm", "2405.hmm"):
+        model = msv.MSV_HMM(msv.Profile_HMM(hmm_path(name)))
+        got = model.parallel_run_on_sequences(resident)
+        assert (ubits(got) == ubits(model.parallel_run_on_sequences(packed))).all()
+        h = oracle.load_hmm(hmm_path(name))
+        table, tr3 = oracle.prepare(h["match_emissions"])
+        want = oracle.score_batch(table, tr3, packed.residues[: int(packed.offsets[200])], packed.offsets[:201].copy(), threads=CORES)
+        assert ubits(got[:200]).tolist() == ubits(want).tolist()
+
+
 def test_single_process_multi_device_driver(oracle):
     """MSV_HMM::parallel_run_on_sequences(db, devices): two slices scored concurrently (here both on GPU 0 when the box
     has one GPU) equal the single-call result."""
