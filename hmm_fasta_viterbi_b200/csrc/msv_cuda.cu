@@ -857,6 +857,20 @@ int msv_cuda_db_filter_device(msv_db* db, const float* scores_device, float mu, 
     return MSV_OK;
 }
 
+int msv_cuda_host_register(const void* buffer, size_t bytes) {
+    if (!buffer || bytes == 0) return MSV_OK;
+    int count = 0;
+    if (int rc = msv_cuda_device_count(&count)) return rc;
+    MSV_CUDA_TRY(cudaHostRegister(const_cast<void*>(buffer), bytes, cudaHostRegisterPortable));
+    return MSV_OK;
+}
+
+int msv_cuda_host_unregister(const void* buffer) {
+    if (!buffer) return MSV_OK;
+    MSV_CUDA_TRY(cudaHostUnregister(const_cast<void*>(buffer)));
+    return MSV_OK;
+}
+
 int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score) {
     if (!score) return fail(MSV_ERR_INVALID_ARGUMENT, "score is NULL");
     const uint64_t offsets[2] = {0, length};

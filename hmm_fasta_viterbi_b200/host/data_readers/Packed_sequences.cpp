@@ -16,6 +16,18 @@ namespace {
 constexpr char letters[] = "ACDEFGHIKLMNPQRSTVWY";
 }
 
+Pinned_sequences::Pinned_sequences(const Packed_sequences& database) {
+    if (msv_cuda_host_register(database.residues.data(), database.residues.size()) == MSV_OK) residues = database.residues.data();
+    if (msv_cuda_host_register(database.offsets.data(), database.offsets.size() * sizeof(uint64_t)) == MSV_OK)
+        offsets = database.offsets.data();
+    // pinning is an optimisation: without a device (or if the driver refuses) the database stays pageable
+}
+
+Pinned_sequences::~Pinned_sequences() {
+    if (residues) msv_cuda_host_unregister(residues);
+    if (offsets) msv_cuda_host_unregister(offsets);
+}
+
 void Packed_sequences::append(const Protein_sequence& seq) {
     const auto skip = static_cast<size_t>(!seq.empty() && seq.front() == '#');
     const auto count = seq.size() - skip;

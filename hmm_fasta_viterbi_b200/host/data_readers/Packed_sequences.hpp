@@ -17,6 +17,22 @@
 
 #include "FASTA_protein_sequences.hpp"
 
+struct Packed_sequences;
+
+// Page-locks the buffers of a Packed_sequences for as long as the guard lives, so that repeated uploads of the same
+// database (one scan per model) run at full link speed.  The database must not be modified or moved meanwhile.
+class Pinned_sequences {
+  public:
+    explicit Pinned_sequences(const Packed_sequences& database);
+    ~Pinned_sequences();
+    Pinned_sequences(const Pinned_sequences&) = delete;
+    Pinned_sequences& operator=(const Pinned_sequences&) = delete;
+
+  private:
+    const void* residues = nullptr;
+    const void* offsets = nullptr;
+};
+
 struct Packed_sequences {
     std::vector<uint8_t> residues;
     std::vector<uint64_t> offsets = {0};

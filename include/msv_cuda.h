@@ -123,6 +123,12 @@ int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t le
 int msv_cuda_db_filter_device(msv_db* db, const float* scores_device, float mu, float lambda, float* bits_device,
                               float* pvalues_device, void* cuda_stream);
 
+/* Page-lock (pin) a caller-owned host buffer so that uploads from it run at full PCIe / C2C speed and overlap with the
+ * scan (msv_cuda_score_batch, msv_cuda_db_create take any host memory; pageable memory is staged by the driver at a
+ * fraction of the link speed).  Registration is expensive (of the order of 1 ms per 4 MB): do it once per database. */
+int msv_cuda_host_register(const void* buffer, size_t bytes);
+int msv_cuda_host_unregister(const void* buffer);
+
 /* kernel launches issued by this library on the calling thread since the last reset (for bench.py's gpu_launches) */
 uint64_t msv_cuda_launch_count(int reset);
 

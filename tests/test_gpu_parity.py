@@ -220,6 +220,23 @@ def test_resident_database_scanned_by_many_models(oracle):
         assert ubits(got[:200]).tolist() == ubits(want).tolist()
 
 
+def test_host_register_round_trip(oracle):
+    """msv_cuda_host_register / _unregister: uploads from a page-locked caller buffer give the same bits."""
+    model, table, tr3 = device_model(oracle, "600.hmm")
+    packed = msv.Packed_sequences.synthetic_swissprot_like(20_000, 31)
+    codes = np.ascontiguousarray(packed.residues).copy()
+    offsets = np.ascontiguousarray(packed.offsets).copy()
+    plain = model.score_batch(codes, offsets)
+    _cabi.check(_cabi.lib.msv_cuda_host_register(codes.ctypes.data, codes.nbytes))
+    _cabi.check(_cabi.lib.msv_cuda_host_register(offsets.ctypes.data, offsets.nbytes))
+    try:
+        pinned = model.score_batch(codes, offsets)
+    finally:
+        _cabi.check(_cabi.lib.msv_cuda_host_unregister(codes.ctypes.data))
+        _cabi.check(_cabi.lib.msv_cuda_host_unregister(offsets.ctypes.data))
+    assert (ubits(plain) == ubits(pinned)).all()
+
+
 def test_single_process_multi_device_driver(oracle):
     """MSV_HMM::parallel_run_on_sequences(db, devices): two slices scored concurrently (here both on GPU 0 when the box
     has one GPU) equal the single-call result."""

@@ -51,6 +51,7 @@ int main(int argc, char** argv) {
         if (entry.path().extension() == ".hmm" && (only.empty() || entry.path().filename() == only)) files.push_back(entry.path());
     std::sort(files.begin(), files.end(), [](const auto& a, const auto& b) { return std::stoi(a.stem()) < std::stoi(b.stem()); });
 
+    const auto pinned = Pinned_sequences(database); // "batch" uploads from page-locked memory
     const auto resident = Device_database(database);
     std::printf("%-10s %6s | %12s %12s %10s | %14s %10s | %12s %10s\n", "model", "LENG", "par us/call", "seq us/call", "par GCUPS",
                 "batch ms", "GCUPS", "resident ms", "GCUPS");
