@@ -29,7 +29,7 @@ DECLARED_SYMBOLS = (
     "msv_cuda_model_create", "msv_cuda_model_destroy", "msv_cuda_model_geometry",
     "msv_cuda_db_create", "msv_cuda_db_destroy", "msv_cuda_db_info",
     "msv_cuda_db_score_device", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
-    "msv_cuda_db_filter_device", "msv_cuda_host_register", "msv_cuda_host_unregister",
+    "msv_cuda_db_filter_device", "msv_cuda_db_score_filter", "msv_cuda_host_register", "msv_cuda_host_unregister",
     "msv_cuda_launch_count",
 )
 
@@ -75,6 +75,7 @@ lib.msv_cuda_db_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.msv_cuda_score_sequence.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, _fp]
 lib.msv_cuda_db_filter_device.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.msv_cuda_db_score_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_host_register.argtypes = [C.c_void_p, C.c_size_t]
 lib.msv_cuda_host_unregister.argtypes = [C.c_void_p]
 lib.msv_cuda_launch_count.restype = C.c_uint64

@@ -174,6 +174,8 @@ struct msv_db {
     uint64_t* d_offsets = nullptr;
     uint32_t* d_order = nullptr;
     float* d_scores = nullptr;
+    float* d_stats = nullptr; // bit scores | P-values, 2 * cap_n, allocated on first use
+    size_t cap_stats = 0;
     size_t cap_n = 0;
     float2* d_length_tr = nullptr;
     size_t cap_tr = 0;
@@ -218,6 +220,7 @@ int db_release(msv_db* db) {
     cudaFree(db->d_offsets);
     cudaFree(db->d_order);
     cudaFree(db->d_scores);
+    cudaFree(db->d_stats);
     cudaFree(db->d_length_tr);
     cudaFree(db->d_hist);
     cudaFree(db->d_queue);
@@ -854,6 +857,31 @@ int msv_cuda_db_filter_device(msv_db* db, const float* scores_device, float mu, 
         scores_device, db->d_offsets, n32, static_cast<double>(mu), static_cast<double>(lambda), bits_device, pvalues_device);
     ++g_launches;
     MSV_CUDA_TRY(cudaGetLastError());
+    return MSV_OK;
+}
+
+int msv_cuda_db_score_filter(msv_model* model, msv_db* db, float mu, float lambda, float* scores_host, float* bits_host,
+                             float* pvalues_host) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (model->device != db->device) return fail(MSV_ERR_INVALID_ARGUMENT, "model and database live on different devices");
+    if (db->n == 0) return MSV_OK;
+    if (!scores_host) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_host is NULL");
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    if (db->cap_stats < db->n) {
+        cudaFree(db->d_stats);
+        db->d_stats = nullptr;
+        db->cap_stats = 0;
+        MSV_CUDA_TRY(cudaMalloc(&db->d_stats, 2 * db->cap_n * sizeof(float)));
+        db->cap_stats = db->cap_n;
+    }
+    float* d_bits = db->d_stats;
+    float* d_p = db->d_stats + db->cap_stats;
+    if (int rc = launch_scan(model, db, 0, db->n, db->total, 0, db->d_scores, nullptr)) return rc;
+    if (int rc = msv_cuda_db_filter_device(db, db->d_scores, mu, lambda, d_bits, d_p, nullptr)) return rc;
+    MSV_CUDA_TRY(cudaMemcpy(scores_host, db->d_scores, db->n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (bits_host) MSV_CUDA_TRY(cudaMemcpy(bits_host, d_bits, db->n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (pvalues_host) MSV_CUDA_TRY(cudaMemcpy(pvalues_host, d_p, db->n * sizeof(float), cudaMemcpyDeviceToHost));
     return MSV_OK;
 }
 

@@ -73,6 +73,8 @@ lib.msvh_device_database_create.restype = _vp
 lib.msvh_device_database_create.argtypes = [_vp, C.c_int]
 lib.msvh_device_database_free.argtypes = [_vp]
 lib.msvh_msv_parallel_run_on_device_database.argtypes = [_vp, _vp, _f32]
+lib.msvh_msv_filter.restype = C.c_long
+lib.msvh_msv_filter.argtypes = [_vp, _vp, C.c_float, C.c_size_t, _vp, _vp, _vp, _vp]
 lib.msvh_msv_parallel_run_on_packed_devices.argtypes = [_vp, _vp, C.POINTER(C.c_int), C.c_int, _f32]
 
 
@@ -242,6 +244,17 @@ class MSV_HMM:
         if status:
             _raise(status)
         return out[: len(database)]
+
+    def msv_filter(self, database: Device_database, threshold: float = 0.02) -> dict:
+        """HMMER3-style MSV filter: sequences with Gumbel P-value <= threshold, as arrays index/score/bits/p_value."""
+        cap = len(database)
+        index = np.empty(max(cap, 1), np.uint64)
+        score, bits, p = (np.empty(max(cap, 1), np.float32) for _ in range(3))
+        found = lib.msvh_msv_filter(self._h, database._h, float(threshold), cap, index.ctypes.data, score.ctypes.data,
+                                    bits.ctypes.data, p.ctypes.data)
+        if found < 0:
+            _raise(int(found))
+        return {"index": index[:found], "score": score[:found], "bits": bits[:found], "p_value": p[:found]}
 
     def __del__(self) -> None:
         if getattr(self, "_h", None):

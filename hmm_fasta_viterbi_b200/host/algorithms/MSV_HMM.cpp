@@ -27,7 +27,8 @@ Device_database::Device_database(const Packed_sequences& database, int device)
 // Model preparation.  All fp32 expressions (log-odds table, B->M_k, E->C, E->J) are evaluated by the shared host
 // helpers of the C ABI so that the C++ class and every other binding produce the same bits as the reference
 // constructor (reference MSV_HMM.cpp:35-53).
-MSV_HMM::MSV_HMM(const Profile_HMM& base_hmm) : model_length(base_hmm.model_length) {
+MSV_HMM::MSV_HMM(const Profile_HMM& base_hmm)
+    : model_length(base_hmm.model_length), msv_mu(base_hmm.stats_local_msv_mu), msv_lambda(base_hmm.stats_local_msv_lambda) {
     emission_scores.resize(NUM_OF_AMINO_ACIDS * model_length);
     if (model_length > 0) {
         msv_host_emission_table(base_hmm.match_emissions.front().data(), model_length, emission_scores.data());
@@ -113,6 +114,19 @@ std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Device_database&
     const auto status = msv_cuda_db_score(on_device(), database.handle(), scores.data());
     if (status != MSV_OK) throw_last_error("MSV_HMM::parallel_run_on_sequences", status);
     return scores;
+}
+
+std::vector<MSV_hit> MSV_HMM::msv_filter(const Device_database& database, float threshold) {
+    if (database.device() != device_index) set_device(database.device());
+    const auto n = database.size();
+    auto scores = std::vector<float>(n), bits = std::vector<float>(n), p_values = std::vector<float>(n);
+    const auto status = msv_cuda_db_score_filter(on_device(), database.handle(), msv_mu, msv_lambda, scores.data(), bits.data(),
+                                                 p_values.data());
+    if (status != MSV_OK) throw_last_error("MSV_HMM::msv_filter", status);
+    auto hits = std::vector<MSV_hit>();
+    for (size_t q = 0; q < n; ++q)
+        if (p_values[q] <= threshold) hits.push_back(MSV_hit{q, scores[q], bits[q], p_values[q]});
+    return hits;
 }
 
 std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Packed_sequences& database, const std::vector<int>& devices) {

@@ -53,6 +53,15 @@ class Device_database {
     int device_index = 0;
 };
 
+// One sequence that passed the MSV filter (HMMER3 conventions: bit score against the null length model, Gumbel
+// P-value with the model's STATS LOCAL MSV parameters).
+struct MSV_hit {
+    size_t sequence;   // index in the database
+    Log_score score;   // raw MSV score, nats (what parallel_run_on_sequence returns)
+    float bits;
+    float p_value;
+};
+
 class MSV_HMM {
   public:
     explicit MSV_HMM(const Profile_HMM& base_hmm);
@@ -70,6 +79,11 @@ class MSV_HMM {
     // GPU, database already resident in HBM (Device_database): only the scores cross PCIe.
     std::vector<Log_score> parallel_run_on_sequences(const Device_database& database);
 
+    // The MSV *filter*: scan, convert to bit scores and P-values on the device, keep sequences with P <= threshold
+    // (HMMER3's default first-stage threshold F1 is 0.02).  The reference parses the model's Gumbel parameters
+    // (Profile_HMM.hpp:34-35) but stops at the raw score.
+    std::vector<MSV_hit> msv_filter(const Device_database& database, float threshold = 0.02f);
+
     // The same over several GPUs of one box from ONE process: the database is cut into contiguous slices of equal
     // cell count, one host thread and one device model per GPU; scores land directly in the result vector, so there
     // is no collective.  (The one-process-per-GPU variant with an NCCL gather is hmm_fasta_viterbi_b200/sharded.py.)
@@ -86,6 +100,7 @@ class MSV_HMM {
     Log_score tr_B_Mk; // B -> M_k, uniform entry
     Log_score tr_E_C;  // E -> C
     Log_score tr_E_J;  // E -> J
+    float msv_mu = 0.0f, msv_lambda = 0.0f; // Gumbel location / slope of MSV bit scores (STATS LOCAL MSV)
 
     int device_index = 0;
     std::shared_ptr<msv_model> device_model; // created on first GPU call, shared by copies

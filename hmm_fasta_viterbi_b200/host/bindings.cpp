@@ -141,6 +141,22 @@ int msvh_msv_parallel_run_on_device_database(void* m, void* d, float* scores) {
     });
 }
 
+// hits are returned as four parallel arrays of capacity `capacity`; the return value is the number of hits (or < 0)
+long msvh_msv_filter(void* m, void* d, float threshold, size_t capacity, uint64_t* index, float* score, float* bits, float* p) {
+    long found = -1;
+    const int status = guarded([&] {
+        const auto hits = static_cast<MSV_HMM*>(m)->msv_filter(*static_cast<Device_database*>(d), threshold);
+        found = static_cast<long>(hits.size());
+        for (size_t i = 0; i < hits.size() && i < capacity; ++i) {
+            index[i] = hits[i].sequence;
+            score[i] = hits[i].score;
+            bits[i] = hits[i].bits;
+            p[i] = hits[i].p_value;
+        }
+    });
+    return status == 0 ? found : status;
+}
+
 int msvh_msv_parallel_run_on_packed_devices(void* m, void* packed, const int* devices, int n_devices, float* scores) {
     return guarded([&] {
         const auto got = static_cast<MSV_HMM*>(m)->parallel_run_on_sequences(*static_cast<Packed_sequences*>(packed),

@@ -123,6 +123,12 @@ int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t le
 int msv_cuda_db_filter_device(msv_db* db, const float* scores_device, float mu, float lambda, float* bits_device,
                               float* pvalues_device, void* cuda_stream);
 
+/* Scan + statistics in one synchronous call on a resident database: raw scores, bit scores and P-values are copied to
+ * the three host arrays (n floats each; bits_host / pvalues_host may be NULL).  This is the body of
+ * MSV_HMM::msv_filter in the C++ layer. */
+int msv_cuda_db_score_filter(msv_model* model, msv_db* db, float mu, float lambda, float* scores_host, float* bits_host,
+                             float* pvalues_host);
+
 /* Page-lock (pin) a caller-owned host buffer so that uploads from it run at full PCIe / C2C speed and overlap with the
  * scan (msv_cuda_score_batch, msv_cuda_db_create take any host memory; pageable memory is staged by the driver at a
  * fraction of the link speed).  Registration is expensive (of the order of 1 ms per 4 MB): do it once per database. */

@@ -220,6 +220,33 @@ def test_resident_database_scanned_by_many_models(oracle):
         assert ubits(got[:200]).tolist() == ubits(want).tolist()
 
 
+def test_msv_filter_keeps_homologs_and_drops_noise(oracle):
+    """MSV_HMM::msv_filter: sequences built from the model's consensus pass the P <= 0.02 filter, almost all random
+    sequences do not; the reported numbers equal an fp64 evaluation of the same formulas."""
+    name = "300.hmm"
+    prof = msv.Profile_HMM(hmm_path(name))
+    model = msv.MSV_HMM(prof)
+    rng = np.random.default_rng(17)
+    cons = prof.match_emissions[1:].argmax(axis=1).astype(np.uint8)
+    noise = [rng.integers(0, 20, size=int(k), dtype=np.uint8) for k in rng.integers(100, 600, size=2000)]
+    homologs = [np.concatenate([rng.integers(0, 20, size=40, dtype=np.uint8), cons[20:280], rng.integers(0, 20, size=40, dtype=np.uint8)])
+                for _ in range(20)]
+    packed = msv.Packed_sequences.from_arrays(*pack(noise + homologs))
+    hits = model.msv_filter(msv.Device_database(packed))
+    found = set(int(i) for i in hits["index"])
+    assert set(range(2000, 2020)) <= found          # every homolog passes
+    assert len(found - set(range(2000, 2020))) < 120  # ~2 % of the noise is expected to pass by chance
+    raw = model.parallel_run_on_sequences(packed).astype(np.float64)
+    L = np.diff(packed.offsets.astype(np.int64)).astype(np.float64)
+    bits = (raw - (L * np.log(L / (L + 1.0)) + np.log(1.0 / (L + 1.0)))) / np.log(2.0)
+    ey = -np.exp(-float(prof.stats_local_msv_lambda) * (bits - float(prof.stats_local_msv_mu)))
+    pv = np.where(np.abs(ey) < 5e-9, -ey, 1.0 - np.exp(ey))
+    idx = hits["index"].astype(np.int64)
+    np.testing.assert_allclose(hits["bits"], bits[idx], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(hits["p_value"], pv[idx], rtol=1e-5, atol=1e-12)
+    assert (pv[idx] <= 0.02 * (1 + 1e-6)).all() and (np.delete(pv, idx) > 0.02 * (1 - 1e-6)).all()
+
+
 def test_host_register_round_trip(oracle):
     """msv_cuda_host_register / _unregister: uploads from a page-locked caller buffer give the same bits."""
     model, table, tr3 = device_model(oracle, "600.hmm")
