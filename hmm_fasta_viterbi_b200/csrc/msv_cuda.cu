@@ -58,7 +58,7 @@ struct Geometry {
     int G, K, KT, threads;
     Scan_kernel fn;         // general transitions
     Scan_kernel fn_cj_same; // tr_E_C == tr_E_J bitwise (C is J); same as fn for the generic family
-    int variant = 0;        // reserved for tuning variants (none at present)
+    int variant = 0;        // 0: tensor-memory columns are each lane's lowest; 1: TMEM_AHEAD (they are the highest, loaded a row ahead)
     size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET) * (K - std::max(KT, 0)) * G * sizeof(float); }
 };
 
@@ -80,6 +80,10 @@ template <int K, int KT, int T> constexpr Geometry warp_entry_threads() {
     return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false>, msv::msv_scan_warp_kernel<K, KT, T, true>};
 }
 
+template <int K, int KT, int T> constexpr Geometry warp_entry_ahead() {
+    return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false, true>, msv::msv_scan_warp_kernel<K, KT, T, true, true>, 1};
+}
+
 #define MSV_FOR_EACH_K(X, A)                                                                                           \
     X(A, 4) X(A, 8) X(A, 12) X(A, 16) X(A, 20) X(A, 24) X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52)  \
     X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) X(A, 76) X(A, 80) X(A, 84) X(A, 88)
@@ -88,6 +92,7 @@ template <int K, int KT, int T> constexpr Geometry warp_entry_threads() {
     X(A, 76) X(A, 80) X(A, 84) X(A, 88)
 #define MSV_GENERIC(G, K) generic_entry<G, K>(),
 #define MSV_WARP(KT, K) warp_entry<K, KT>(),
+#define MSV_WARP_AHEAD(KT, K) warp_entry_ahead<K, KT, warp_threads_for(K, KT)>(),
 #define MSV_FOR_EACH_K_FROM_28(X, A)                                                                                   \
     X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) X(A, 76)  \
     X(A, 80) X(A, 84) X(A, 88)
@@ -96,7 +101,9 @@ const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(M
                                          MSV_WARP(16, 16) MSV_WARP(16, 20) MSV_WARP(24, 24) MSV_FOR_EACH_K_FROM_24(MSV_WARP, 16)
                                              MSV_FOR_EACH_K_FROM_28(MSV_WARP, 24) MSV_WARP(0, 44) MSV_WARP(8, 44)
                                                  warp_entry_threads<44, 16, 640>(), warp_entry_threads<44, 16, 448>(),
-                                 warp_entry_threads<44, 16, 384>(),
+                                 warp_entry_threads<44, 16, 384>(), MSV_FOR_EACH_K_FROM_24(MSV_WARP_AHEAD, 16)
+                                     MSV_FOR_EACH_K_FROM_28(MSV_WARP_AHEAD, 24) MSV_WARP_AHEAD(16, 16) MSV_WARP_AHEAD(16, 20)
+                                         MSV_WARP_AHEAD(8, 8) MSV_WARP_AHEAD(8, 12)
                                  quad_entry<4, 0>(), quad_entry<8, 8>(), quad_entry<12, 8>(), quad_entry<16, 16>(), quad_entry<20, 16>(),
                                  quad_entry<24, 16>(), quad_entry<28, 16>(), quad_entry<32, 16>(), quad_entry<36, 16>(),
                                  quad_entry<40, 24>(), quad_entry<44, 24>()};
@@ -122,13 +129,31 @@ const Geometry* choose_geometry(size_t columns) {
         if (got >= 3 && static_cast<size_t>(G) * K > columns)
             if (const Geometry* g = find_geometry(G, K, KT, T, V)) return g;
     }
-    // Measured on B200 over the 24 fixture models (profiles/r01/sweep_models_v2.jsonl, sweep_kt_v2.jsonl): the
-    // warp-per-sequence kernel with the shared-memory/tensor-memory split wins at every model length, with 16 tensor-memory
-    // columns per lane (24 for the longest rows, 8 or none for the shortest).
+    // Measured on B200 over the 24 fixture models (profiles/r01/sweep_models_v2.jsonl, sweep_kt_v2.jsonl,
+    // sweep_tmem_ahead_models.jsonl): the warp-per-sequence kernel with the shared-memory/tensor-memory split wins at every
+    // model length; how many columns per lane come from tensor memory, and whether they are loaded a row ahead
+    // (variant 1), is picked per K from those sweeps.
     const int K = std::max(4, round_up4((columns + 1 + 31) / 32)); // 32*K > columns: lane 31 ends in a padding column
     if (K > msv::kMaxColumnsPerLane) return nullptr;
-    const int KT = K >= 72 ? 24 : K >= 16 ? 16 : K >= 8 ? 8 : 0;
-    return find_geometry(32, K, KT);
+    struct Choice {
+        int KT, variant;
+    };
+    const auto pick = [](int k) -> Choice {
+        switch (k) {
+        case 4: return {0, 0};
+        case 8: case 12: return {8, 1};
+        case 16: return {16, 1};
+        case 20: return {16, 0};
+        case 24: case 28: return {16, 1};
+        case 32: case 36: return {24, 1};
+        case 40: return {16, 1};
+        case 44: return {16, 0};
+        case 48: case 52: case 56: return {16, 1};
+        default: return {24, 1}; // 60 .. 88
+        }
+    };
+    const Choice choice = pick(K);
+    return find_geometry(32, K, choice.KT, 0, choice.variant);
 }
 
 // Eight lanes per sequence (four sequences per warp) pays off for short models: measured on B200
@@ -713,12 +738,14 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
             const size_t col = static_cast<size_t>(g) * K + j + 1;
             return col <= columns ? emission_scores[res * model_length + col] : -std::numeric_limits<float>::infinity();
         };
+        const bool tensor_high = geo->variant == 1; // TMEM_AHEAD kernels keep the tensor-memory columns at the top of a lane
+        const int shared_first = tensor_high ? 0 : KT, tensor_first = tensor_high ? KS : 0;
         for (int res = 0; res < MSV_ALPHABET; ++res)
             for (int g = 0; g < G; ++g) {
                 for (int js = 0; js < KS; ++js)
-                    laid[((static_cast<size_t>(res) * (KS / 4) + js / 4) * G + g) * 4 + js % 4] = emission(res, g, KT + js);
+                    laid[((static_cast<size_t>(res) * (KS / 4) + js / 4) * G + g) * 4 + js % 4] = emission(res, g, shared_first + js);
                 for (int jt = 0; jt < KT; ++jt)
-                    laid[shared_floats + (static_cast<size_t>(res) * G + g) * KT + jt] = emission(res, g, jt);
+                    laid[shared_floats + (static_cast<size_t>(res) * G + g) * KT + jt] = emission(res, g, tensor_first + jt);
             }
         plan.table_bytes = laid.size() * sizeof(float);
         plan.shared_bytes = geo->shared_bytes();

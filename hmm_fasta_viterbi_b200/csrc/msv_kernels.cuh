@@ -310,7 +310,10 @@ template <int KT> __device__ __forceinline__ void tmem_wait(float* v) {
 //   * when tr_E_C and tr_E_J are the same bits (always, for the reference's nu = 2, MSV_HMM.cpp:49-53) the C and J
 //     recurrences are the same function of the same inputs, so C == J and only J is carried (CJ_SAME);
 //   * one FMNMX3 chain accumulates E; max(N+move, J+move) is computed as max(N, J)+move (rounding is monotone).
-template <int K, int KT, int THREADS, bool CJ_SAME>
+//   * TMEM_AHEAD: the tensor-memory columns are the TOP KT columns of each lane and their emissions for row i+1 are
+//     requested while row i is still being computed, so every row starts on operands that are already in registers
+//     (instead of waiting for the first LDS) and the shared-memory loads of the row land behind that work.
+template <int K, int KT, int THREADS, bool CJ_SAME, bool TMEM_AHEAD = false>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_params p) {
     static_assert(KT == 0 || KT == 8 || KT == 16 || KT == 24, "TMEM columns per lane");
     constexpr int KS = K - KT;
@@ -398,33 +401,49 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         for (int j = 0; j < K; ++j) m[j] = NEG_INF; // MSV_HMM.cpp:86
         float J = NEG_INF, C = NEG_INF, N = 0.0f, B = move; // MSV_HMM.cpp:96-97
 
-        auto row = [&](const uint32_t x) {
-            float te[KT > 0 ? KT : 1];
-            if constexpr (KT > 0) tmem_load<KT>(tmem_lane_base + x * KT, te);
+        float te[KT > 0 ? KT : 1]; // emissions of the tensor-memory columns for the row at hand
+        auto row = [&](const uint32_t x, const uint32_t x_next) {
+            constexpr bool AHEAD = TMEM_AHEAD && KT > 0;
+            if constexpr (KT > 0 && !AHEAD) tmem_load<KT>(tmem_lane_base + x * KT, te);
             const uint32_t erow = tab_lane + x * ROW_BYTES;
             const float bt = B + tBMk; // MSV_HMM.cpp:103, B -> M_k entry
             // lane 0 receives lane 31's last column, which is padding and therefore -inf: the dummy column M0
             const float left = __shfl_sync(0xffffffffu, m[K - 1], left_lane);
             float e = NEG_INF;
+            // columns are updated from the highest down; TB / SB = first column served by tensor / shared memory
+            constexpr int TB = AHEAD ? KS : 0, SB = AHEAD ? 0 : KT;
+            const auto tensor_columns = [&] {
+                if constexpr (KT > 0) {
+                    tmem_wait<KT>(te);
 #pragma unroll
-            for (int q = KS / 4 - 1; q >= 0; --q) {
-                const float4 ev = lds128(erow + q * 512);
-                const int j = KT + 4 * q;
-                m[j + 3] = ev.w + fmaxf(m[j + 2], bt);
-                m[j + 2] = ev.z + fmaxf(m[j + 1], bt);
-                m[j + 1] = ev.y + fmaxf(m[j], bt);
-                m[j] = ev.x + fmaxf(j ? m[j > 0 ? j - 1 : 0] : left, bt);
-                e = fmaxf(fmaxf(e, m[j + 3]), m[j + 2]); // MSV_HMM.cpp:104
-                e = fmaxf(fmaxf(e, m[j + 1]), m[j]);
-            }
-            if constexpr (KT > 0) {
-                tmem_wait<KT>(te);
-#pragma unroll
-                for (int j = KT - 1; j >= 1; j -= 2) {
-                    m[j] = te[j] + fmaxf(m[j - 1], bt);
-                    m[j - 1] = te[j - 1] + fmaxf(j > 1 ? m[j > 1 ? j - 2 : 0] : left, bt);
-                    e = fmaxf(fmaxf(e, m[j]), m[j - 1]);
+                    for (int jj = KT - 1; jj >= 1; jj -= 2) {
+                        const int j = TB + jj;
+                        m[j] = te[jj] + fmaxf(m[j - 1], bt);
+                        m[j - 1] = te[jj - 1] + fmaxf(j > 1 ? m[j > 1 ? j - 2 : 0] : left, bt);
+                        e = fmaxf(fmaxf(e, m[j]), m[j - 1]); // MSV_HMM.cpp:104
+                    }
                 }
+            };
+            const auto shared_columns = [&] {
+#pragma unroll
+                for (int q = KS / 4 - 1; q >= 0; --q) {
+                    const float4 ev = lds128(erow + q * 512);
+                    const int j = SB + 4 * q;
+                    m[j + 3] = ev.w + fmaxf(m[j + 2], bt);
+                    m[j + 2] = ev.z + fmaxf(m[j + 1], bt);
+                    m[j + 1] = ev.y + fmaxf(m[j], bt);
+                    m[j] = ev.x + fmaxf(j ? m[j > 0 ? j - 1 : 0] : left, bt);
+                    e = fmaxf(fmaxf(e, m[j + 3]), m[j + 2]);
+                    e = fmaxf(fmaxf(e, m[j + 1]), m[j]);
+                }
+            };
+            if constexpr (AHEAD) {
+                tensor_columns();
+                tmem_load<KT>(tmem_lane_base + x_next * KT, te); // for the next row; lands while this row finishes
+                shared_columns();
+            } else {
+                shared_columns();
+                tensor_columns();
             }
             float E;
             asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(E) : "f"(e));
@@ -434,28 +453,32 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
             B = fmaxf(N, J) + move; // MSV_HMM.cpp:110: max(N+move, J+move) == max(N, J)+move exactly (rounding is monotone)
         };
 
-        // residues arrive as aligned 32-bit words (4 per load, one word prefetched ahead); a funnel shift undoes the
-        // byte misalignment of the sequence start
+        // residues arrive as aligned 32-bit words (4 per load, prefetched two words ahead); a funnel shift undoes the
+        // byte misalignment of the sequence start.  `word` holds the next four residues, `ahead` the four after them.
         const uint32_t shift = (static_cast<uint32_t>(begin) & 3u) * 8u;
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues + (begin & ~static_cast<uint64_t>(3)));
-        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
-        wp += 2;
+        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+        wp += 3;
+        uint32_t word = __funnelshift_r(w0, w1, shift);
+        if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + (word & 0xffu) * KT, te);
         const uint32_t quads = len >> 2;
 #pragma unroll 1
         for (uint32_t i = 0; i < quads; ++i) {
-            const uint32_t word = __funnelshift_r(w0, w1, shift);
-            w0 = w1;
-            w1 = __ldg(wp);
+            const uint32_t ahead = __funnelshift_r(w1, w2, shift);
+            w1 = w2;
+            w2 = __ldg(wp);
             ++wp;
-            row(__byte_perm(word, 0, 0x4440));
-            row(__byte_perm(word, 0, 0x4441));
-            row(__byte_perm(word, 0, 0x4442));
-            row(__byte_perm(word, 0, 0x4443));
+            const uint32_t x0 = __byte_perm(word, 0, 0x4440), x1 = __byte_perm(word, 0, 0x4441);
+            const uint32_t x2 = __byte_perm(word, 0, 0x4442), x3 = __byte_perm(word, 0, 0x4443);
+            row(x0, x1);
+            row(x1, x2);
+            row(x2, x3);
+            row(x3, __byte_perm(ahead, 0, 0x4440));
+            word = ahead;
         }
-        uint32_t word = __funnelshift_r(w0, w1, shift);
 #pragma unroll 1
         for (uint32_t r = len & 3u; r > 0; --r) {
-            row(word & 0xffu);
+            row(word & 0xffu, (word >> 8) & 0xffu);
             word >>= 8;
         }
         if (lane == 0) p.scores[idx] = (CJ_SAME ? J : C) + move; // MSV_HMM.cpp:112

@@ -102,6 +102,9 @@ def test_homologous_sequences_exercise_the_J_state(oracle):
                                        # warp kernels: shared memory + KT tensor-memory columns per lane
                                        "32,4,0", "32,8,0", "32,8,8", "32,20,8", "32,24,16", "32,28,16", "32,44,0", "32,44,8",
                                        "32,44,16", "32,44,24", "32,44,16,640", "32,64,16", "32,76,16", "32,76,24", "32,88,16",
+                                       # warp kernels with the tensor-memory columns loaded a row ahead (variant 1)
+                                       "32,8,8,0,1", "32,16,16,0,1", "32,28,16,0,1", "32,36,24,0,1", "32,44,16,0,1",
+                                       "32,60,24,0,1", "32,76,24,0,1", "32,88,24,0,1",
                                        # quad kernels: four warps (128 lanes) per sequence
                                        "128,4,0", "128,8,8", "128,12,8", "128,16,16", "128,20,16", "128,28,16", "128,36,16",
                                        "128,40,24", "128,44,24"])
