@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--model", default=MODEL_FILE)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the bounded baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short config-3 / config-5 side measurements")
     return ap.parse_args()
 
 
@@ -177,6 +178,46 @@ def workload_config(args, leng: int) -> dict:
     return {"workload": f"config4: {args.model} (LENG {leng}) x {args.sequences} synthetic Swiss-Prot-like sequences "
                         f"per {'GPU' if args.scaling == 'weak' else 'job'}, mt19937_64 seed {SEED}(+rank)",
             "model": args.model, "sequences": args.sequences, "l2": "inputs larger than L2 (≈347 MB residues per scan)"}
+
+
+def other_configs(torch, msv, _cabi, device: int) -> dict:
+    """Side measurements on the same GPU, outside the headline's timed region (device-resident scans, CUDA events):
+    BASELINE.json config 3 (every fixture model x 100k sequences) and config 5 (2405.hmm x 2048 titin-like sequences)."""
+    stream = torch.cuda.current_stream()
+
+    def gcups(model, db, n, leng, residues, steps=3):
+        scores = torch.empty(n, dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            db.score_device(model, scores, stream.cuda_stream)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for _ in range(steps):
+            db.score_device(model, scores, stream.cuda_stream)
+        t1.record(stream)
+        torch.cuda.synchronize()
+        return leng * float(residues) / (t0.elapsed_time(t1) / steps) / 1e6
+
+    def load(name):
+        prof = msv.Profile_HMM(os.path.join(REPO, "fixtures", "profile_HMMs", name))
+        return prof.model_length - 1, msv.Model(_cabi.emission_table(prof.match_emissions), *_cabi.model_transitions(prof.model_length),
+                                                 device=device)
+
+    sweep_db = msv.Packed_sequences.synthetic_swissprot_like(100_000, 1400)
+    resident = msv.Database(sweep_db.residues, sweep_db.offsets, device=device)
+    names = sorted((f for f in os.listdir(os.path.join(REPO, "fixtures", "profile_HMMs")) if f.endswith(".hmm")),
+                   key=lambda s: int(s.split(".")[0]))
+    config3 = {}
+    for name in names:
+        leng, model = load(name)
+        config3[name] = round(gcups(model, resident, len(sweep_db), leng, sweep_db.total_residues), 1)
+        model.close()
+    long_db = msv.Packed_sequences.synthetic_long_uniform(2048, 2405, 10_000, 35_000)
+    long_resident = msv.Database(long_db.residues, long_db.offsets, device=device)
+    leng, model = load("2405.hmm")
+    config5 = round(gcups(model, long_resident, len(long_db), leng, long_db.total_residues), 1)
+    return {"unit": "GCUPS, device-resident", "config3_model_sweep_100k_sequences": config3,
+            "config5_2405hmm_2048_long_sequences": config5}
 
 
 # ---- our arm ----------------------------------------------------------------------------------------------------------
@@ -353,6 +394,8 @@ def main() -> None:
             }
             parity["oracle_checked"] = int(nN)
             parity["oracle_mismatches"] = int((result[:nN].view(np.uint32) != np.asarray(sN, np.float32).view(np.uint32)).sum())
+        if world == 1 and not args.no_other_configs:
+            out["other_configs"] = other_configs(torch, msv, _cabi, local)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
