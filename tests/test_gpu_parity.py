@@ -174,6 +174,28 @@ def test_models_longer_than_one_warp(oracle, leng):
     assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
 
 
+@pytest.mark.parametrize("leng,seed", [(1, 0), (2, 1), (31, 2), (32, 3), (33, 4), (127, 5), (128, 6), (129, 7), (447, 8), (448, 9), (1023, 10)])
+def test_synthetic_models_with_impossible_emissions(oracle, leng, seed):
+    """Random models whose match emissions contain exact zeros (log-odds -inf) and ones, at lengths that sit on the
+    kernel-geometry boundaries; the eight-lane, warp and four-warp plans all have to propagate -inf exactly."""
+    rng = np.random.default_rng(seed)
+    match = synthetic_model(rng, leng)
+    match[1:][rng.random((leng, 20)) < 0.15] = 0.0   # impossible residues
+    match[1:][rng.random((leng, 20)) < 0.02] = 1.0   # "*" fields of a .hmm file parse as probability 1.0
+    table, tr3 = oracle.prepare(match)
+    model = msv.Model(_cabi.emission_table(match), *_cabi.model_transitions(leng + 1))
+    seqs, codes, offsets = random_db(rng, 400, 0, 120)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+    big = msv.Packed_sequences.synthetic_swissprot_like(30_000, seed)     # large enough for the bulk / eight-lane plans
+    got = msv.Database(big.residues, big.offsets).score(model)
+    sample = rng.choice(len(big), size=120, replace=False)
+    off = big.offsets
+    sc, so = pack([big.residues[int(off[q]):int(off[q + 1])] for q in sample])
+    want = oracle.score_batch(table, tr3, sc, so, threads=CORES)
+    assert ubits(got[sample]).tolist() == ubits(want).tolist()
+
+
 def test_model_beyond_on_chip_capacity_is_refused(oracle):
     rng = np.random.default_rng(1)
     match = synthetic_model(rng, 5700)
