@@ -148,6 +148,24 @@ def test_reference_reader_tests_pass_unchanged(prog):
     assert run.returncode == 0, run.stdout + run.stderr
 
 
+@pytest.mark.timeout(600)
+def test_host_layer_under_address_and_ub_sanitizers(tmp_path):
+    """tests/host_selftest.cpp, compiled together with the host sources with -fsanitize=address,undefined."""
+    host = os.path.join(REPO, "hmm_fasta_viterbi_b200", "host")
+    sources = [os.path.join(host, "data_readers", f) for f in
+               ("Profile_HMM.cpp", "FASTA_protein_sequences.cpp", "Packed_sequences.cpp", "Synthetic_database.cpp")]
+    sources += [os.path.join(host, "algorithms", "MSV_HMM.cpp"), os.path.join(REPO, "tests", "host_selftest.cpp")]
+    exe = str(tmp_path / "host_selftest")
+    pkg = os.path.join(REPO, "hmm_fasta_viterbi_b200")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                    f"-I{host}/data_readers", f"-I{host}/algorithms", f"-I{REPO}/include", *sources, "-o", exe,
+                    f"-L{pkg}", "-lmsv_cuda", "-lpthread", f"-Wl,-rpath,{pkg}"], check=True)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:protect_shadow_gap=0", UBSAN_OPTIONS="print_stacktrace=1")
+    run = subprocess.run([exe, os.path.join(REPO, "fixtures"), str(tmp_path)], capture_output=True, text=True, env=env, timeout=500)
+    assert run.returncode == 0, run.stdout[-3000:] + run.stderr[-3000:]
+    assert "host selftest ok" in run.stdout
+
+
 def test_partition_by_cells():
     rng = np.random.default_rng(3)
     lens = rng.integers(0, 500, size=1000)
