@@ -24,12 +24,12 @@
 #include "Packed_sequences.hpp"
 #include "Profile_HMM.hpp"
 
-using Log_score = float;
+typedef float Log_score; // natural-log odds, fp32 like the reference
 
+// aliases of the reference's header that no caller uses; kept so that code naming them still compiles
 template <int N> using Log_scores_array = std::array<Log_score, N>;
 template <int N> using Log_scores_arrays_vector = std::vector<Log_scores_array<N>>;
-
-using Kernels_source_code = std::string; // kept for source compatibility; kernels are compiled in, nothing is read at run time
+typedef std::string Kernels_source_code; // kernels are compiled in; nothing is read at run time
 
 struct msv_model; // opaque device model of the C ABI
 struct msv_db;    // opaque device-resident database of the C ABI

@@ -12,38 +12,32 @@
 #include <string_view>
 #include <vector>
 
-constexpr int NUM_OF_AMINO_ACIDS = 20;
-constexpr int NUM_OF_TRANSITIONS = 7;
+enum : int { NUM_OF_AMINO_ACIDS = 20, NUM_OF_TRANSITIONS = 7 }; // columns of an emission row / a transition row
 
-using Probability = float;
-using Profile_name = std::string;
+typedef float Probability;
+typedef std::string Profile_name;
 
 template <int N> using Probabilities_array = std::array<Probability, N>;
 template <int N> using Probabilities_arrays_vector = std::vector<Probabilities_array<N>>;
 
-class Profile_HMM {
-  public:
+struct Profile_HMM {
     // Parse `file_path`.  On an unreadable file a message goes to stdout and the object stays empty
     // (model_length == 0), which is what the reference does (Profile_HMM.cpp:49-53).
     explicit Profile_HMM(const std::string& file_path);
 
     Profile_name name;
+    size_t model_length = 0; // LENG + 1 (counts the begin node)
 
     // Row i describes node i of the model; row 0 is the begin node: match_emissions[0] is all zero,
     // insert_emissions[0] / transitions[0] come from the two lines that follow COMPO.
     // Values are probabilities, exp(-x) of the file's negative natural logs.
-    Probabilities_arrays_vector<NUM_OF_AMINO_ACIDS> match_emissions;
-    Probabilities_arrays_vector<NUM_OF_AMINO_ACIDS> insert_emissions;
+    Probabilities_arrays_vector<NUM_OF_AMINO_ACIDS> match_emissions, insert_emissions;
     Probabilities_arrays_vector<NUM_OF_TRANSITIONS> transitions; // m->m m->i m->d i->m i->i d->m d->d
-    size_t model_length = 0;                                     // LENG + 1 (counts the begin node)
 
     // STATS LOCAL lines: Gumbel location/slope for MSV and Viterbi scores, exponential tail for Forward scores.
-    float stats_local_msv_mu = 0.0f;
-    float stats_local_msv_lambda = 0.0f;
-    float stats_local_viterbi_mu = 0.0f;
-    float stats_local_viterbi_lambda = 0.0f;
-    float stats_local_forward_theta = 0.0f;
-    float stats_local_forward_lambda = 0.0f;
+    float stats_local_msv_mu = 0.0f, stats_local_msv_lambda = 0.0f;
+    float stats_local_viterbi_mu = 0.0f, stats_local_viterbi_lambda = 0.0f;
+    float stats_local_forward_theta = 0.0f, stats_local_forward_lambda = 0.0f;
 
   private:
     // Consumes the text of one .hmm file; returns false when a mandatory section is missing.
