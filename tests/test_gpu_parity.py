@@ -272,6 +272,35 @@ def test_msv_filter_keeps_homologs_and_drops_noise(oracle):
     assert (pv[idx] <= 0.02 * (1 + 1e-6)).all() and (np.delete(pv, idx) > 0.02 * (1 - 1e-6)).all()
 
 
+def test_handles_release_device_memory(oracle):
+    """Creating, using and destroying models / databases / workspaces repeatedly leaves the free device memory where
+    it was (every plan's table, the workspace buffers, streams and events are released)."""
+    import torch
+
+    h = oracle.load_hmm(hmm_path("1400.hmm"))
+    table = _cabi.emission_table(h["match_emissions"])
+    tr = _cabi.model_transitions(h["model_length"])
+    packed = msv.Packed_sequences.synthetic_swissprot_like(5000, 77)
+
+    def cycle():
+        model = msv.Model(table, *tr)
+        model.score_batch(packed.residues, packed.offsets)
+        db = msv.Database(packed.residues, packed.offsets)
+        db.score(model)
+        db.close()
+        model.close()
+
+    for _ in range(3):
+        cycle()
+    torch.cuda.synchronize()
+    before = torch.cuda.mem_get_info()[0]
+    for _ in range(60):
+        cycle()
+    torch.cuda.synchronize()
+    after = torch.cuda.mem_get_info()[0]
+    assert before - after < 8 * 2**20, (before, after)
+
+
 def test_host_register_round_trip(oracle):
     """msv_cuda_host_register / _unregister: uploads from a page-locked caller buffer give the same bits."""
     model, table, tr3 = device_model(oracle, "600.hmm")
