@@ -301,6 +301,26 @@ def test_handles_release_device_memory(oracle):
     assert before - after < 8 * 2**20, (before, after)
 
 
+def test_msv_scan_command_line(oracle):
+    """build/msv_scan --all: the printed raw scores are the reference bits for the fixture FASTA file."""
+    exe = os.path.join(REPO, "build", "msv_scan")
+    if not os.path.exists(exe):
+        pytest.skip("build/msv_scan not built")
+    run = subprocess.run([exe, "--all", hmm_path("100.hmm"), hmm_path("1400.hmm"), fasta_path("fasta_like_example.fsa")],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    rows = [ln.split("\t") for ln in run.stdout.splitlines() if not ln.startswith("#")]
+    assert len(rows) == 8
+    h = oracle.load_hmm(hmm_path("100.hmm"))
+    table, tr3 = oracle.prepare(h["match_emissions"])
+    seqs = oracle.load_fasta(fasta_path("fasta_like_example.fsa"))
+    for row, seq in zip(rows[:4], seqs):
+        assert row[0] == "Pfam-B_229" and int(row[2]) == len(seq) - 1
+        assert abs(float(row[3]) - float(oracle.score_string(table, tr3, seq))) < 1e-4 * abs(float(row[3]))
+    missing = subprocess.run([exe, "/nonexistent.hmm", fasta_path("fasta_like_example.fsa")], capture_output=True, text=True)
+    assert missing.returncode == 1
+
+
 def test_host_register_round_trip(oracle):
     """msv_cuda_host_register / _unregister: uploads from a page-locked caller buffer give the same bits."""
     model, table, tr3 = device_model(oracle, "600.hmm")

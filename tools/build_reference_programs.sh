@@ -21,6 +21,8 @@ CXX=${CXX:-g++}
 mkdir -p "$OUT"
 $CXX -std=c++20 -O2 -Wall -Wextra -I"$HOST/algorithms" -I"$HOST/data_readers" -I"$ROOT/include" "$ROOT/tools/msv_bench.cpp" \
     -o "$OUT/msv_bench" -L"$PKG" -lmsv_host -lmsv_cuda -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../hmm_fasta_viterbi_b200'
+$CXX -std=c++20 -O2 -Wall -Wextra -I"$HOST/algorithms" -I"$HOST/data_readers" -I"$ROOT/include" "$ROOT/tools/msv_scan.cpp" \
+    -o "$OUT/msv_scan" -L"$PKG" -lmsv_host -lmsv_cuda -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../hmm_fasta_viterbi_b200'
 
 [ -d "$REF/algorithms" ] || { echo "reference tree $REF not present; keeping prebuilt build/ (if any)"; exit 0; }
 mkdir -p "$OUT/algorithms" "$OUT/data_readers"
