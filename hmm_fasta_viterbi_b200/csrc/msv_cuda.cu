@@ -104,6 +104,10 @@ const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(M
                                  warp_entry_threads<44, 16, 384>(), MSV_FOR_EACH_K_FROM_24(MSV_WARP_AHEAD, 16)
                                      MSV_FOR_EACH_K_FROM_28(MSV_WARP_AHEAD, 24) MSV_WARP_AHEAD(16, 16) MSV_WARP_AHEAD(16, 20)
                                          MSV_WARP_AHEAD(8, 8) MSV_WARP_AHEAD(8, 12)
+                                 // columns per lane in steps of two (less padding): tensor-memory part 18 = 16 + 2 columns
+                                 MSV_WARP_AHEAD(6, 6) MSV_WARP_AHEAD(10, 10) MSV_WARP_AHEAD(14, 14) MSV_WARP_AHEAD(18, 18) MSV_WARP_AHEAD(18, 22)
+                                 MSV_WARP_AHEAD(18, 26) MSV_WARP_AHEAD(18, 30) MSV_WARP_AHEAD(18, 34) MSV_WARP_AHEAD(18, 38) MSV_WARP_AHEAD(18, 42)
+                                 MSV_WARP_AHEAD(18, 46) MSV_WARP_AHEAD(18, 50) MSV_WARP_AHEAD(18, 54) MSV_WARP_AHEAD(18, 58)
                                  quad_entry<4, 0>(), quad_entry<8, 8>(), quad_entry<12, 8>(), quad_entry<16, 16>(), quad_entry<20, 16>(),
                                  quad_entry<24, 16>(), quad_entry<28, 16>(), quad_entry<32, 16>(), quad_entry<36, 16>(),
                                  quad_entry<40, 24>(), quad_entry<44, 24>()};
@@ -133,12 +137,17 @@ const Geometry* choose_geometry(size_t columns) {
     // sweep_tmem_ahead_models.jsonl): the warp-per-sequence kernel with the shared-memory/tensor-memory split wins at every
     // model length; how many columns per lane come from tensor memory, and whether they are loaded a row ahead
     // (variant 1), is picked per K from those sweeps.
-    const int K = std::max(4, round_up4((columns + 1 + 31) / 32)); // 32*K > columns: lane 31 ends in a padding column
+    // 32*K > columns (lane 31 ends in a padding column).  K moves in steps of two up to 58 (less padding: +2..7 % on the
+    // fixture models, profiles/r01/sweep_models_v5_even_k.jsonl) and in steps of four beyond (there the 18-column tensor
+    // part of the odd steps spills registers and loses to the next multiple of four).
+    int K = std::max(4, static_cast<int>((columns + 1 + 63) / 64 * 2));
+    if (K > 58) K = round_up4(K);
     if (K > msv::kMaxColumnsPerLane) return nullptr;
     struct Choice {
         int KT, variant;
     };
     const auto pick = [](int k) -> Choice {
+        if (k % 4 == 2) return {k <= 18 ? k : 18, 1}; // columns per lane in steps of two: 18 = 16 + 2 tensor-memory columns
         switch (k) {
         case 4: return {0, 0};
         case 8: case 12: return {8, 1};

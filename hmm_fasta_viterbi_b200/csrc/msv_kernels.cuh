@@ -250,12 +250,6 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
 // it is in flight, tcgen05.wait::ld, then the TMEM columns.  The address must be warp-uniform, which is why this
 // variant exists for G == 32 only (all lanes of the warp scan the same residue).
 // =====================================================================================================================
-__device__ __forceinline__ void tmem_store8(uint32_t taddr, const float* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(v[0]),
-                 "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
-}
-
 __device__ __forceinline__ void tmem_load8(uint32_t taddr, float* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
@@ -281,22 +275,40 @@ __device__ __forceinline__ void tmem_wait16(float* v) {
                    "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])::"memory");
 }
 
-template <int KT> __device__ __forceinline__ void tmem_load(uint32_t taddr, float* v) {
-    static_assert(KT == 8 || KT == 16 || KT == 24, "TMEM columns per lane");
-    if constexpr (KT == 8) tmem_load8(taddr, v);
-    if constexpr (KT == 16) tmem_load16(taddr, v);
-    if constexpr (KT == 24) {
-        tmem_load16(taddr, v);
-        tmem_load8(taddr + 16, v + 16);
-    }
+__device__ __forceinline__ void tmem_store2(uint32_t taddr, float a, float b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(a), "f"(b) : "memory");
 }
+__device__ __forceinline__ void tmem_load2(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_load4(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait2(float* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1])::"memory");
+}
+__device__ __forceinline__ void tmem_wait4(float* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3])::"memory");
+}
+
+// KT (even, <= 24) columns per lane as a sum of power-of-two pieces: 24 = 16+8, 18 = 16+2, 14 = 8+4+2, ...
+template <int KT> __device__ __forceinline__ void tmem_load(uint32_t taddr, float* v) {
+    static_assert(KT >= 2 && KT <= 24 && KT % 2 == 0, "TMEM columns per lane");
+    constexpr int P = KT >= 16 ? 16 : KT >= 8 ? 8 : KT >= 4 ? 4 : 2;
+    if constexpr (P == 16) tmem_load16(taddr, v);
+    if constexpr (P == 8) tmem_load8(taddr, v);
+    if constexpr (P == 4) tmem_load4(taddr, v);
+    if constexpr (P == 2) tmem_load2(taddr, v);
+    if constexpr (KT > P) tmem_load<KT - P>(taddr + P, v + P);
+}
+// (the waits after the first are free: tcgen05.wait::ld covers every earlier load)
 template <int KT> __device__ __forceinline__ void tmem_wait(float* v) {
-    if constexpr (KT == 8) tmem_wait8(v);
-    if constexpr (KT == 16) tmem_wait16(v);
-    if constexpr (KT == 24) {
-        tmem_wait16(v);
-        tmem_wait8(v + 16); // second wait is free: everything has already landed
-    }
+    constexpr int P = KT >= 16 ? 16 : KT >= 8 ? 8 : KT >= 4 ? 4 : 2;
+    if constexpr (P == 16) tmem_wait16(v);
+    if constexpr (P == 8) tmem_wait8(v);
+    if constexpr (P == 4) tmem_wait4(v);
+    if constexpr (P == 2) tmem_wait2(v);
+    if constexpr (KT > P) tmem_wait<KT - P>(v + P);
 }
 
 // Table in global memory for this kernel:
@@ -315,9 +327,9 @@ template <int KT> __device__ __forceinline__ void tmem_wait(float* v) {
 //     (instead of waiting for the first LDS) and the shared-memory loads of the row land behind that work.
 template <int K, int KT, int THREADS, bool CJ_SAME, bool TMEM_AHEAD = false>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_params p) {
-    static_assert(KT == 0 || KT == 8 || KT == 16 || KT == 24, "TMEM columns per lane");
+    static_assert(KT >= 0 && KT <= 24 && KT % 2 == 0, "TMEM columns per lane");
     constexpr int KS = K - KT;
-    static_assert(K % 4 == 0 && KS >= 0 && KS % 4 == 0 && K <= kMaxColumnsPerLane, "columns per lane");
+    static_assert(K % 2 == 0 && KS >= 0 && KS % 4 == 0 && K <= kMaxColumnsPerLane, "columns per lane");
     constexpr uint32_t ROW_BYTES = KS * 32 * 4;
     constexpr uint32_t SMEM_TABLE_BYTES = kAlphabet * ROW_BYTES;
     constexpr uint32_t COPY_CHUNK = 32768;
@@ -365,11 +377,9 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
                 reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(p.table) + SMEM_TABLE_BYTES);
             for (int x = 0; x < kAlphabet; ++x) {
 #pragma unroll
-                for (int c = 0; c < KT / 8; ++c) {
-                    const float4 a = __ldg(src + ((x * 32 + lane) * KT + 8 * c) / 4);
-                    const float4 b = __ldg(src + ((x * 32 + lane) * KT + 8 * c) / 4 + 1);
-                    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                    tmem_store8(tmem_lane_base + x * KT + 8 * c, v);
+                for (int c = 0; c < KT / 2; ++c) {
+                    const float2 a = __ldg(reinterpret_cast<const float2*>(src) + ((x * 32 + lane) * KT + 2 * c) / 2);
+                    tmem_store2(tmem_lane_base + x * KT + 2 * c, a.x, a.y);
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -562,12 +572,9 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_quad_kernel(const Scan_pa
                 reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(p.table) + SMEM_TABLE_BYTES);
             for (int x = 0; x < kAlphabet; ++x) {
 #pragma unroll
-                for (int c = 0; c < KT / 8; ++c) {
-                    const int at = ((x * 128 + wq * 32 + lane) * KT + 8 * c) / 4;
-                    const float4 a = __ldg(src + at);
-                    const float4 b = __ldg(src + at + 1);
-                    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                    tmem_store8(tmem_lane_base + x * KT + 8 * c, v);
+                for (int c = 0; c < KT / 2; ++c) {
+                    const float2 a = __ldg(reinterpret_cast<const float2*>(src) + ((x * 128 + wq * 32 + lane) * KT + 2 * c) / 2);
+                    tmem_store2(tmem_lane_base + x * KT + 2 * c, a.x, a.y);
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

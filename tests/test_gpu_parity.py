@@ -105,6 +105,9 @@ def test_homologous_sequences_exercise_the_J_state(oracle):
                                        # warp kernels with the tensor-memory columns loaded a row ahead (variant 1)
                                        "32,8,8,0,1", "32,16,16,0,1", "32,28,16,0,1", "32,36,24,0,1", "32,44,16,0,1",
                                        "32,60,24,0,1", "32,76,24,0,1", "32,88,24,0,1",
+                                       # columns per lane in steps of two (tensor part 6/10/14/18 = sums of 16, 8, 4, 2)
+                                       "32,6,6,0,1", "32,10,10,0,1", "32,14,14,0,1", "32,18,18,0,1", "32,22,18,0,1", "32,42,18,0,1",
+                                       "32,58,18,0,1",
                                        # quad kernels: four warps (128 lanes) per sequence
                                        "128,4,0", "128,8,8", "128,12,8", "128,16,16", "128,20,16", "128,28,16", "128,36,16",
                                        "128,40,24", "128,44,24"])
