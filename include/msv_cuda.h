@@ -80,9 +80,10 @@ int msv_host_partition_by_cells(const uint64_t* offsets, size_t n, int parts, si
 int msv_cuda_model_create(const float* emission_scores, size_t model_length, float tr_B_Mk, float tr_E_C, float tr_E_J,
                           int device, msv_model** out);
 int msv_cuda_model_destroy(msv_model* model);
-/* kernel geometry chosen for this model: lanes per sequence (8/16/32), model columns per lane, how many of those
- * columns are served from tensor memory (TMEM; -1 = kernel family without TMEM), threads per CTA, dynamic shared
- * memory bytes.  Any pointer may be NULL. */
+/* geometry of the model's throughput plan: lanes per sequence (32 = one warp, 128 = four warps when the model is too
+ * long for one warp; a model may also carry an 8-lane plan for short models and a 128-lane plan for few/long sequences,
+ * chosen per launch), model columns per lane, how many of those columns are served from tensor memory (TMEM; -1 = kernel
+ * family without TMEM), threads per CTA, dynamic shared memory bytes.  Any pointer may be NULL. */
 int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane,
                             int* tensor_columns_per_lane, int* threads_per_cta, size_t* shared_bytes);
 
@@ -96,7 +97,9 @@ int msv_cuda_db_destroy(msv_db* db);
 int msv_cuda_db_info(const msv_db* db, size_t* n, uint64_t* total_residues, uint64_t* longest);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Scoring.  One kernel launch scores the whole database.
+ * Scoring.  One kernel launch scores a resident database (msv_cuda_score_batch issues one launch per upload stage so
+ * that the copy engine and the scan overlap).  Limits: model_length - 1 <= 5631 columns, sequences < 2^27 residues,
+ * fewer than 2^32 - 1 sequences per database.
  * ------------------------------------------------------------------------------------------------------------- */
 /* resident path: scores_device is a DEVICE pointer to n floats (original sequence order); asynchronous on
  * `cuda_stream` (a cudaStream_t passed as void*, NULL = default stream). */
