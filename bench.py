@@ -362,6 +362,10 @@ def main() -> None:
             "peak_source": f"{sms} SMs x 128 fp32 lanes x {sm_max_mhz:.0f} MHz (max SM clock); 3 lane-ops per cell",
             "kernel_ms": kernel_ms, "kernel_gcups": kernel_gcups, "gcups_at_alu_roofline": alu_peak * 1e3 / LANE_OPS_PER_CELL,
             "smem_ceiling_gcups": sms * 32 * sm_max_mhz * 1e6 / 1e9,
+            # register-only add+max mix measured on this GPU type (tools/microbench.cu, profiles/r01/microbench_b200.json):
+            # 38.5 cells/clk/SM -- the FMNMX pipe runs at half rate, so this is the practical ALU ceiling
+            "measured_mix_peak_gcups": sms * 38.52 * sm_max_mhz * 1e6 / 1e9,
+            "frac_of_measured_mix_peak": kernel_gcups / (sms * 38.52 * sm_max_mhz * 1e6 / 1e9),
             "hbm": {"achieved": hbm_bytes / (kernel_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": hbm_bytes / (kernel_ms / 1e3) / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6650"},
