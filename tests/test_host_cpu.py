@@ -51,6 +51,7 @@ def test_cabi_carries_sm100a_code_with_tma():
     assert "UBLKCP" in sass       # cp.async.bulk: the emission table is staged by the TMA unit
     assert "CREDUX.MAX.F32" in sass  # warp-wide fp32 max of the E reduction
     assert "FMNMX3" in sass
+    assert "LDTM" in sass and "STTM" in sass  # tcgen05.ld / tcgen05.st: part of the emission table lives in tensor memory
 
 
 @pytest.mark.skipif(not NO_GPU, reason="only meaningful on a box without a GPU")
