@@ -459,6 +459,25 @@ def test_full_size_properties_config4(oracle):
     assert (ubits(model.score_batch(rc, ro)) == ubits(first[sl])).all()
 
 
+def test_full_size_sample_parity_config3(oracle):
+    """Every fixture model x 100 000 synthetic sequences (config 3), default plan selection: a seeded sample of each
+    scan is compared with the oracle, and the resident and host-buffer paths agree on all 100 000 scores."""
+    packed = msv.Packed_sequences.synthetic_swissprot_like(100_000, 1400)
+    codes, offsets = packed.residues, packed.offsets
+    resident = msv.Database(codes, offsets)
+    rng = np.random.default_rng(3)
+    sample = rng.choice(len(packed), size=48, replace=False)
+    sc, so = pack([codes[int(offsets[q]):int(offsets[q + 1])] for q in sample])
+    for name in model_files():
+        model, table, tr3 = device_model(oracle, name)
+        got = resident.score(model)
+        want = oracle.score_batch(table, tr3, sc, so, threads=CORES)
+        assert ubits(got[sample]).tolist() == ubits(want).tolist(), name
+        if name in ("100.hmm", "400.hmm", "900.hmm", "2405.hmm"):
+            assert (ubits(model.score_batch(codes, offsets)) == ubits(got)).all(), name
+        model.close()
+
+
 def test_full_size_properties_config5(oracle):
     """2405.hmm x long sequences (config 5 shape, 256 sequences): determinism and a sample against the oracle."""
     model, table, tr3 = device_model(oracle, "2405.hmm")
