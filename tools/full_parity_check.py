@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""One-off, exhaustive parity check at the headline size: every one of the 1 000 000 scores of the bench workload
+(1400.hmm x synthetic Swiss-Prot-like database, seed 20261018) is compared bit-for-bit with the CPU checker (the
+reference's own code from oracle/_ref when present, else the C restatement).  Takes ~1.5 minutes on 16 host threads."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [REPO, os.path.join(REPO, "tests")]
+import hmm_fasta_viterbi_b200 as msv  # noqa: E402
+from hmm_fasta_viterbi_b200 import _cabi  # noqa: E402
+from oracle_lib import Oracle, RefLib  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+model_path = os.path.join(REPO, "fixtures", "profile_HMMs", "1400.hmm")
+prof = msv.Profile_HMM(model_path)
+model = msv.Model(_cabi.emission_table(prof.match_emissions), *_cabi.model_transitions(prof.model_length))
+db = msv.Packed_sequences.synthetic_swissprot_like(n, 20261018)
+gpu = model.score_batch(db.residues, db.offsets)
+threads = os.cpu_count() or 1
+t0 = time.perf_counter()
+if RefLib.available():
+    kind = "reference (oracle/_ref)"
+    cpu = RefLib().model(model_path).run_batch(db.residues, db.offsets, threads)
+else:
+    kind = "port (oracle/msv_oracle.c)"
+    oracle = Oracle()
+    table, tr3 = oracle.prepare(oracle.load_hmm(model_path)["match_emissions"])
+    cpu = oracle.score_batch(table, tr3, db.residues, db.offsets, threads)
+seconds = time.perf_counter() - t0
+mismatches = int((gpu.view(np.uint32) != np.asarray(cpu, np.float32).view(np.uint32)).sum())
+print(json.dumps({"sequences": n, "residues": int(db.total_residues), "model": "1400.hmm", "checker": kind, "cpu_threads": threads,
+                  "cpu_seconds": round(seconds, 1), "mismatches": mismatches, "geometry": model.geometry}))
+sys.exit(1 if mismatches else 0)
