@@ -15,11 +15,15 @@ import hmm_fasta_viterbi_b200 as msv  # noqa: E402
 from hmm_fasta_viterbi_b200 import _cabi  # noqa: E402
 from oracle_lib import Oracle, RefLib  # noqa: E402
 
+# usage: full_parity_check.py [sequences] [model.hmm] [long]      ("long": config-5 style sequences of 10-35 k residues)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-model_path = os.path.join(REPO, "fixtures", "profile_HMMs", "1400.hmm")
+model_name = sys.argv[2] if len(sys.argv) > 2 else "1400.hmm"
+long_sequences = len(sys.argv) > 3 and sys.argv[3] == "long"
+model_path = os.path.join(REPO, "fixtures", "profile_HMMs", model_name)
 prof = msv.Profile_HMM(model_path)
 model = msv.Model(_cabi.emission_table(prof.match_emissions), *_cabi.model_transitions(prof.model_length))
-db = msv.Packed_sequences.synthetic_swissprot_like(n, 20261018)
+db = (msv.Packed_sequences.synthetic_long_uniform(n, 2405, 10_000, 35_000) if long_sequences
+      else msv.Packed_sequences.synthetic_swissprot_like(n, 20261018))
 gpu = model.score_batch(db.residues, db.offsets)
 threads = os.cpu_count() or 1
 t0 = time.perf_counter()
@@ -33,6 +37,6 @@ else:
     cpu = oracle.score_batch(table, tr3, db.residues, db.offsets, threads)
 seconds = time.perf_counter() - t0
 mismatches = int((gpu.view(np.uint32) != np.asarray(cpu, np.float32).view(np.uint32)).sum())
-print(json.dumps({"sequences": n, "residues": int(db.total_residues), "model": "1400.hmm", "checker": kind, "cpu_threads": threads,
+print(json.dumps({"sequences": n, "residues": int(db.total_residues), "model": model_name, "long_sequences": long_sequences, "checker": kind, "cpu_threads": threads,
                   "cpu_seconds": round(seconds, 1), "mismatches": mismatches, "geometry": model.geometry}))
 sys.exit(1 if mismatches else 0)
