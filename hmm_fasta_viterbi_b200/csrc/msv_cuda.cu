@@ -815,6 +815,14 @@ int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int
     return MSV_OK;
 }
 
+int msv_cuda_model_plan(const msv_model* model, const msv_db* db, int* lanes_per_sequence, int* sequences_per_cta) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    const Launch_plan chosen = plan_launch(model, db, 0, db->n, db->total);
+    if (lanes_per_sequence) *lanes_per_sequence = chosen.plan->geo->G;
+    if (sequences_per_cta) *sequences_per_cta = static_cast<int>(chosen.slots_per_cta);
+    return MSV_OK;
+}
+
 // ---- database -------------------------------------------------------------------------------------------------------
 int msv_cuda_db_create(int device, const uint8_t* residues, const uint64_t* offsets, size_t n, msv_db** out) {
     if (!out) return fail(MSV_ERR_INVALID_ARGUMENT, "out is NULL");

@@ -87,6 +87,10 @@ int msv_cuda_model_destroy(msv_model* model);
 int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane,
                             int* tensor_columns_per_lane, int* threads_per_cta, size_t* shared_bytes);
 
+/* which launch plan a scan of the whole of `db` with `model` would use (introspection for tests and tuning): lanes per
+ * sequence of the chosen kernel family (8, 32 or 128) and sequences in flight per CTA.  Does not launch anything. */
+int msv_cuda_model_plan(const msv_model* model, const msv_db* db, int* lanes_per_sequence, int* sequences_per_cta);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Database (device resident).  Uploads residues + offsets, validates the codes, computes the per-length
  * tr_loop/tr_move table on the host, and buckets the sequences longest-first on the device.

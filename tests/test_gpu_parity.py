@@ -207,6 +207,23 @@ def test_model_beyond_on_chip_capacity_is_refused(oracle):
     assert err.value.status == _cabi.MSV_ERR_MODEL_TOO_LONG
 
 
+def test_launch_planner_choices(oracle):
+    """The planner picks the kernel family and occupancy from the shape of the database (msv_cuda_model_plan)."""
+    big, _, _ = device_model(oracle, "1400.hmm")
+    short, _, _ = device_model(oracle, "300.hmm")
+    one = msv.Database(np.zeros(3500, np.uint8), np.array([0, 3500], np.uint64))
+    assert big.plan(one) == {"lanes_per_sequence": 128, "sequences_per_cta": 1}          # one sequence: four warps, one SM
+    many = msv.Packed_sequences.synthetic_swissprot_like(150_000, 1)
+    many_db = msv.Database(many.residues, many.offsets)
+    assert big.plan(many_db) == {"lanes_per_sequence": 32, "sequences_per_cta": 16}      # bulk: a warp each, 16 warps per SM
+    assert short.plan(many_db)["lanes_per_sequence"] == 8                                # short model, many sequences: 8 lanes each
+    titin = msv.Packed_sequences.synthetic_long_uniform(2048, 2405, 10_000, 35_000)     # config 5: fewer sequences than warp slots
+    plan = big.plan(msv.Database(titin.residues, titin.offsets))
+    assert plan["lanes_per_sequence"] == 32 and plan["sequences_per_cta"] in (8, 12)     # a warp each at reduced occupancy
+    few_short = msv.Packed_sequences.synthetic_swissprot_like(500, 2)
+    assert big.plan(msv.Database(few_short.residues, few_short.offsets))["lanes_per_sequence"] == 128
+
+
 def test_few_long_sequences_use_four_warps_each(oracle):
     """Below two sequences per warp slot the library switches to the quad plan by itself; same bits either way."""
     model, table, tr3 = device_model(oracle, "1400.hmm")
