@@ -51,7 +51,7 @@ int fail(int code, const char* fmt, ...) {
 //   generic : G = 8/16/32 lanes per sequence, whole table in shared memory           (KT = -1 below)
 //   warp    : G = 32, table split between shared memory and KT tensor-memory columns per lane (KT = 0, 8, 16, 24)
 constexpr int threads_for(int K) { return K <= 20 ? 1024 : K <= 40 ? 768 : K <= 56 ? 640 : 512; }
-constexpr int warp_threads_for(int K, int KT) { return K + (KT > 0 ? 8 : 0) <= 24 ? 1024 : K <= 28 ? 768 : K <= 36 ? 640 : 512; }
+constexpr int warp_threads_for(int K, int KT) { return K + (KT > 0 ? 8 : 0) <= 24 ? 1024 : K <= 30 ? 768 : K <= 36 ? 640 : 512; }
 
 using Scan_kernel = void (*)(const msv::Scan_params);
 struct Geometry {
