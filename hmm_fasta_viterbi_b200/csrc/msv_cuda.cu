@@ -156,7 +156,7 @@ const Geometry* choose_geometry(size_t columns) {
         case 24: case 28: return {16, 1};
         case 32: case 36: return {24, 1};
         case 40: return {16, 1};
-        case 44: return {16, 0};
+        case 44: return {24, 1};
         case 48: case 52: case 56: return {16, 1};
         default: return {24, 1}; // 60 .. 88
         }
