@@ -472,10 +472,12 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         uint32_t word = __funnelshift_r(w0, w1, shift);
         if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + (word & 0xffu) * KT, te);
         const uint32_t quads = len >> 2;
-        // 4 rows (one residue word) per loop iteration, 8 or 16 where B200 sweeps showed a gain
-        // (profiles/r01/sweep_models_v6_row_unroll.jsonl: +10 % at K = 4, +1..2 % at K = 30, 36, 42, 44; the longer bodies
-        // of K >= 48 stop fitting the instruction cache: -10 % at K = 76)
-        constexpr int WORD_UNROLL = K == 4 ? 4 : (K == 30 || K == 32 || K == 36 || K == 42 || K == 44) ? 2 : 1;
+        // 4 rows (one residue word) per loop iteration, 8 or 16 where B200 sweeps showed a gain (+1..4 %, +10 % at K = 4;
+        // profiles/r01/sweep_models_v6_row_unroll.jsonl, sweep_force_unroll2.txt).  It is not monotone in K -- the
+        // instruction scheduler's luck -- and the longest bodies stop fitting the instruction cache (-10 % at K = 76).
+        constexpr bool EIGHT_ROWS = K == 20 || K == 30 || K == 32 || K == 36 || K == 42 || K == 44 || K == 52 || K == 54 || K == 58 ||
+                                    K == 60 || K == 68;
+        constexpr int WORD_UNROLL = K == 4 ? 4 : EIGHT_ROWS ? 2 : 1;
 #pragma unroll WORD_UNROLL
         for (uint32_t i = 0; i < quads; ++i) {
             const uint32_t ahead = __funnelshift_r(w1, w2, shift);
