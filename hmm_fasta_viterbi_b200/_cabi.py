@@ -31,6 +31,8 @@ DECLARED_SYMBOLS = (
     "msv_cuda_db_score_device", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
     "msv_cuda_db_filter_device", "msv_cuda_db_score_filter", "msv_cuda_host_register", "msv_cuda_host_unregister",
     "msv_cuda_launch_count",
+    "msv_host_viterbi_transitions", "msv_cuda_viterbi_model_create", "msv_cuda_viterbi_model_destroy",
+    "msv_cuda_viterbi_model_geometry", "msv_cuda_db_viterbi_device", "msv_cuda_db_viterbi", "msv_cuda_viterbi_batch",
 )
 
 
@@ -79,6 +81,14 @@ lib.msv_cuda_db_filter_device.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c
 lib.msv_cuda_db_score_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_host_register.argtypes = [C.c_void_p, C.c_size_t]
 lib.msv_cuda_host_unregister.argtypes = [C.c_void_p]
+lib.msv_host_viterbi_transitions.argtypes = [_f32, C.c_size_t, _f32]
+lib.msv_cuda_viterbi_model_create.argtypes = [_f32, _f32, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_int,
+                                              C.POINTER(C.c_void_p)]
+lib.msv_cuda_viterbi_model_destroy.argtypes = [C.c_void_p]
+lib.msv_cuda_viterbi_model_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+lib.msv_cuda_db_viterbi_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.msv_cuda_db_viterbi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+lib.msv_cuda_viterbi_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.msv_cuda_launch_count.restype = C.c_uint64
 lib.msv_cuda_launch_count.argtypes = [C.c_int]
 for _name in DECLARED_SYMBOLS:
@@ -119,6 +129,14 @@ def length_transitions(residues: int) -> tuple[np.float32, np.float32]:
     a, b = C.c_float(), C.c_float()
     check(lib.msv_host_length_transitions(residues, C.byref(a), C.byref(b)))
     return np.float32(a.value), np.float32(b.value)
+
+
+def viterbi_transitions(transitions: np.ndarray) -> np.ndarray:
+    """logf of the node transition probabilities Profile_HMM parses ([model_length][7])."""
+    t = np.ascontiguousarray(transitions, np.float32)
+    out = np.empty_like(t)
+    check(lib.msv_host_viterbi_transitions(t, t.shape[0], out))
+    return out
 
 
 def encode(letters: str) -> np.ndarray:
@@ -203,6 +221,45 @@ class Model:
             pass
 
 
+class ViterbiModel:
+    """Device-resident model of the Plan-7 local Viterbi scan (msv_viterbi_model*)."""
+
+    def __init__(self, emission_scores: np.ndarray, log_transitions: np.ndarray, tr_B_Mk, tr_E_C, tr_E_J, device: int = 0) -> None:
+        table = np.ascontiguousarray(emission_scores, np.float32)
+        logtr = np.ascontiguousarray(log_transitions, np.float32)
+        assert table.ndim == 2 and table.shape[0] == 20 and logtr.shape == (table.shape[1], 7)
+        self.model_length = int(table.shape[1])
+        self.device = device
+        h = C.c_void_p()
+        check(lib.msv_cuda_viterbi_model_create(table, logtr, self.model_length, float(tr_B_Mk), float(tr_E_C), float(tr_E_J),
+                                                device, C.byref(h)))
+        self.handle = h
+
+    @property
+    def geometry(self) -> dict:
+        k, t, s = C.c_int(), C.c_int(), C.c_size_t()
+        check(lib.msv_cuda_viterbi_model_geometry(self.handle, C.byref(k), C.byref(t), C.byref(s)))
+        return {"lanes_per_sequence": 32, "columns_per_lane": k.value, "threads_per_cta": t.value, "shared_bytes": s.value}
+
+    def score_batch(self, residues, offsets, out=None) -> np.ndarray:
+        n = len(offsets) - 1
+        if out is None:
+            out = np.empty(n, np.float32)
+        check(lib.msv_cuda_viterbi_batch(self.handle, _ptr(residues), _ptr(offsets), n, _ptr(out)))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            lib.msv_cuda_viterbi_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Database:
     """Device-resident packed database (msv_db*)."""
 
@@ -230,6 +287,14 @@ class Database:
     def score_device(self, model: Model, scores_device, stream: int = 0) -> None:
         """Asynchronous scan into a device buffer (torch CUDA tensor or raw pointer) on `stream`."""
         check(lib.msv_cuda_db_score_device(model.handle, self.handle, _ptr(scores_device), stream))
+
+    def viterbi(self, model: "ViterbiModel") -> np.ndarray:
+        out = np.empty(self.n, np.float32)
+        check(lib.msv_cuda_db_viterbi(model.handle, self.handle, out.ctypes.data))
+        return out
+
+    def viterbi_device(self, model: "ViterbiModel", scores_device, stream: int = 0) -> None:
+        check(lib.msv_cuda_db_viterbi_device(model.handle, self.handle, _ptr(scores_device), stream))
 
     def filter_device(self, scores_device, mu: float, lam: float, bits_device=None, pvalues_device=None, stream: int = 0) -> None:
         """Bit scores and Gumbel P-values (HMMER3 MSV filter conventions) from raw scores resident on the device."""

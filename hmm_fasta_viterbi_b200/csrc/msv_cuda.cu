@@ -17,13 +17,13 @@
 #include <string>
 #include <vector>
 
+#include "msv_internal.hpp"
 #include "msv_kernels.cuh"
 
-namespace {
+static thread_local std::string g_last_error;
+static thread_local uint64_t g_launches = 0;
 
-thread_local std::string g_last_error;
-thread_local uint64_t g_launches = 0;
-
+namespace msv_detail {
 int fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -33,18 +33,10 @@ int fail(int code, const char* fmt, ...) {
     g_last_error = buf;
     return code;
 }
+void count_launch() { ++g_launches; }
+} // namespace msv_detail
 
-#define MSV_CUDA_TRY(expr)                                                                                             \
-    do {                                                                                                               \
-        cudaError_t err__ = (expr);                                                                                    \
-        if (err__ != cudaSuccess) {                                                                                    \
-            const int code__ = (err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver) ? MSV_ERR_NO_DEVICE \
-                               : (err__ == cudaErrorMemoryAllocation)                               ? MSV_ERR_OUT_OF_MEMORY \
-                                                                                                    : MSV_ERR_CUDA;    \
-            (void)cudaGetLastError();                                                                                  \
-            return fail(code__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__);        \
-        }                                                                                                              \
-    } while (0)
+namespace {
 
 // ---- kernel registry ------------------------------------------------------------------------------------------------
 // Two kernel families (msv_kernels.cuh):
@@ -181,49 +173,9 @@ const Geometry* choose_quad_geometry(size_t columns) {
     return nullptr;
 }
 
-struct Device_guard {
-    int previous = -1;
-    cudaError_t status;
-    explicit Device_guard(int device) {
-        status = cudaGetDevice(&previous);
-        if (status == cudaSuccess && previous != device) status = cudaSetDevice(device);
-    }
-    ~Device_guard() {
-        if (previous >= 0) (void)cudaSetDevice(previous);
-    }
-};
-
 } // namespace
 
 // ---- opaque handles ---------------------------------------------------------------------------------------------
-constexpr int kMaxChunks = 32; // pipelined upload: at most this many upload/scan stages per batch
-struct msv_db {
-    int device = 0;
-    size_t n = 0;
-    uint64_t total = 0;
-    uint64_t longest = 0;
-    // device buffers (grow-only capacities so a workspace database can be refilled without reallocating)
-    uint8_t* d_residues = nullptr;
-    size_t cap_residues = 0;
-    uint64_t* d_offsets = nullptr;
-    uint32_t* d_order = nullptr;
-    float* d_scores = nullptr;
-    float* d_stats = nullptr; // bit scores | P-values, 2 * cap_n, allocated on first use
-    size_t cap_stats = 0;
-    size_t cap_n = 0;
-    float2* d_length_tr = nullptr;
-    size_t cap_tr = 0;
-    uint32_t* d_hist = nullptr; // hist | cursor, 2 * kBuckets
-    unsigned int* d_queue = nullptr;
-    unsigned long long* d_first_bad = nullptr;
-    std::vector<float2> h_length_tr; // host copy, extended lazily
-    std::vector<uint32_t> h_lengths; // sequence lengths, kept on the host only for small databases (launch planning)
-    // pipelined upload (msv_cuda_score_batch): copy engine and scan overlap
-    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
-    cudaEvent_t stage_copied[kMaxChunks] = {};
-    cudaEvent_t reserved = nullptr;
-};
-
 struct msv_model {
     int device = 0;
     size_t model_length = 0;

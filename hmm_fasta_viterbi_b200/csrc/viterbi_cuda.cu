@@ -1,0 +1,233 @@
+// viterbi_cuda.cu -- the msv_cuda_viterbi_* part of the C ABI (include/msv_cuda.h): model upload for the Plan-7 local
+// Viterbi scan and its dispatch over a device-resident database.  Kernels: viterbi_kernels.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <vector>
+
+#include "msv_internal.hpp"
+#include "viterbi_kernels.cuh"
+
+namespace {
+
+using Scan_kernel = void (*)(const msv::Scan_params);
+struct Viterbi_geometry {
+    int K, threads;
+    Scan_kernel fn, fn_cj_same;
+    size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 * sizeof(float); }
+    size_t table_floats() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 + 32 * 5 * static_cast<size_t>(K) + 32 * 4; }
+};
+
+// three state registers per column: the register file, not shared memory, bounds the warps per SM
+constexpr int viterbi_threads_for(int K) { return K <= 8 ? 768 : K <= 16 ? 512 : K <= 24 ? 384 : K <= 56 ? 256 : 224; }
+template <int K> constexpr Viterbi_geometry viterbi_entry() {
+    return Viterbi_geometry{K, viterbi_threads_for(K), msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), false>,
+                            msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), true>};
+}
+const Viterbi_geometry k_viterbi_geometries[] = {
+    viterbi_entry<4>(),  viterbi_entry<8>(),  viterbi_entry<12>(), viterbi_entry<16>(), viterbi_entry<20>(),
+    viterbi_entry<24>(), viterbi_entry<28>(), viterbi_entry<32>(), viterbi_entry<36>(), viterbi_entry<40>(),
+    viterbi_entry<44>(), viterbi_entry<48>(), viterbi_entry<52>(), viterbi_entry<56>(), viterbi_entry<60>(),
+    viterbi_entry<64>(), viterbi_entry<68>(), viterbi_entry<72>(), viterbi_entry<76>(), viterbi_entry<80>(),
+};
+
+const Viterbi_geometry* choose_viterbi_geometry(size_t model_length) {
+    // 32 * K slots hold columns 0 .. LENG (column 0 is the dummy the recurrence needs at its left end)
+    for (const Viterbi_geometry& g : k_viterbi_geometries)
+        if (static_cast<size_t>(g.K) * 32 >= model_length) return &g;
+    return nullptr;
+}
+
+} // namespace
+
+struct msv_viterbi_model {
+    int device = 0;
+    size_t model_length = 0;
+    const Viterbi_geometry* geo = nullptr;
+    float4* d_table = nullptr;
+    float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
+    int sm_count = 0;
+};
+
+extern "C" {
+
+int msv_host_viterbi_transitions(const float* transitions, size_t model_length, float* log_transitions) {
+    if (!transitions || !log_transitions) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
+    for (size_t i = 0; i < model_length * MSV_TRANSITIONS; ++i) log_transitions[i] = logf(transitions[i]);
+    return MSV_OK;
+}
+
+int msv_cuda_viterbi_model_create(const float* emission_scores, const float* log_transitions, size_t model_length, float tr_B_Mk,
+                                  float tr_E_C, float tr_E_J, int device, msv_viterbi_model** out) {
+    if (!out) return fail(MSV_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!emission_scores || !log_transitions || model_length < 1) return fail(MSV_ERR_INVALID_ARGUMENT, "empty model");
+    for (size_t i = 0; i < model_length * MSV_TRANSITIONS; ++i)
+        if (!(log_transitions[i] <= 0.0f)) // also rejects NaN
+            return fail(MSV_ERR_INVALID_ARGUMENT, "log_transitions[%zu] = %g is not the logarithm of a probability", i,
+                        static_cast<double>(log_transitions[i]));
+    int count = 0;
+    if (int rc = msv_cuda_device_count(&count)) return rc;
+    if (count == 0) return fail(MSV_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= count) return fail(MSV_ERR_INVALID_ARGUMENT, "device %d out of range (have %d)", device, count);
+    const Viterbi_geometry* geo = choose_viterbi_geometry(model_length);
+    if (!geo)
+        return fail(MSV_ERR_MODEL_TOO_LONG, "Viterbi: model of %zu columns exceeds 32 lanes x %d columns", model_length - 1,
+                    msv::kViterbiMaxColumnsPerLane);
+
+    Device_guard guard(device);
+    MSV_CUDA_TRY(guard.status);
+    cudaDeviceProp prop{};
+    MSV_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MSV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < geo->shared_bytes() + 1024)
+        return fail(MSV_ERR_MODEL_TOO_LONG, "Viterbi: tables of a %zu-column model exceed shared memory", model_length - 1);
+
+    // kernel layout, see viterbi_kernels.cuh.  Slot s = lane * K + j holds model column s - pad (right aligned).
+    const int K = geo->K;
+    const long columns = static_cast<long>(model_length) - 1; // LENG
+    const long pad = 32L * K - 1 - columns;
+    const float ninf = -std::numeric_limits<float>::infinity();
+    enum { MM = 0, MI = 1, MD = 2, IM = 3, II = 4, DM = 5, DD = 6 }; // order of Profile_HMM::transitions (Profile_HMM.hpp:29)
+    const auto tr = [&](long node, int which) { return log_transitions[node * MSV_TRANSITIONS + which]; };
+    const auto from_left = [&](long slot, int which) { // transition `which` of the column left of `slot`, into `slot`
+        const long c = slot - pad;
+        return (c >= 2 && c <= columns) ? tr(c - 1, which) : ninf;
+    };
+    const auto own = [&](long slot, int which) { // insert-state transitions of the column in `slot` (there is no I_LENG)
+        const long c = slot - pad;
+        return (c >= 1 && c <= columns - 1) ? tr(c, which) : ninf;
+    };
+    std::vector<float> laid(geo->table_floats(), ninf);
+    const size_t row = static_cast<size_t>(K) * 32;
+    float* md = laid.data() + MSV_ALPHABET * row;
+    float* dd = md + row;
+    float* tensor = dd + row;
+    float* edge = tensor + 32 * 5 * static_cast<size_t>(K);
+    for (int lane = 0; lane < 32; ++lane) {
+        for (int j = 0; j < K; ++j) {
+            const long slot = static_cast<long>(lane) * K + j, c = slot - pad;
+            const int q = j / 4, w = j % 4;
+            const size_t at = (static_cast<size_t>(q) * 32 + lane) * 4 + w;
+            for (int res = 0; res < MSV_ALPHABET; ++res)
+                laid[res * row + at] = (c >= 1 && c <= columns) ? emission_scores[res * model_length + c] : ninf;
+            md[at] = from_left(slot, MD);
+            dd[at] = from_left(slot, DD);
+            float* t = tensor + (static_cast<size_t>(lane) * (K / 4) + q) * 20;
+            t[w] = from_left(slot, MM);
+            t[4 + w] = from_left(slot, IM);
+            t[8 + w] = from_left(slot, DM);
+            t[12 + w] = own(slot, MI);
+            t[16 + w] = own(slot, II);
+        }
+        const long next = static_cast<long>(lane + 1) * K;
+        edge[lane * 4 + 0] = lane < 31 ? from_left(next, MM) : ninf;
+        edge[lane * 4 + 1] = lane < 31 ? from_left(next, IM) : ninf;
+        edge[lane * 4 + 2] = lane < 31 ? from_left(next, DM) : ninf;
+        edge[lane * 4 + 3] = from_left(static_cast<long>(lane) * K, DD);
+    }
+
+    auto* model = new (std::nothrow) msv_viterbi_model();
+    if (!model) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+    model->device = device;
+    model->model_length = model_length;
+    model->geo = geo;
+    model->tr_B_Mk = tr_B_Mk;
+    model->tr_E_C = tr_E_C;
+    model->tr_E_J = tr_E_J;
+    model->sm_count = prop.multiProcessorCount;
+    cudaError_t err = cudaMalloc(&model->d_table, laid.size() * sizeof(float));
+    if (err == cudaSuccess) err = cudaMemcpy(model->d_table, laid.data(), laid.size() * sizeof(float), cudaMemcpyHostToDevice);
+    for (Scan_kernel fn : {geo->fn, geo->fn_cj_same})
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(geo->shared_bytes()));
+    if (err != cudaSuccess) {
+        cudaFree(model->d_table);
+        delete model;
+        (void)cudaGetLastError();
+        return fail(err == cudaErrorMemoryAllocation ? MSV_ERR_OUT_OF_MEMORY : MSV_ERR_CUDA, "Viterbi model upload failed: %s",
+                    cudaGetErrorString(err));
+    }
+    *out = model;
+    return MSV_OK;
+}
+
+int msv_cuda_viterbi_model_destroy(msv_viterbi_model* model) {
+    if (!model) return MSV_OK;
+    {
+        Device_guard guard(model->device);
+        cudaFree(model->d_table);
+    }
+    delete model;
+    return MSV_OK;
+}
+
+int msv_cuda_viterbi_model_geometry(const msv_viterbi_model* model, int* columns_per_lane, int* threads_per_cta, size_t* shared_bytes) {
+    if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
+    if (columns_per_lane) *columns_per_lane = model->geo->K;
+    if (threads_per_cta) *threads_per_cta = model->geo->threads;
+    if (shared_bytes) *shared_bytes = model->geo->shared_bytes();
+    return MSV_OK;
+}
+
+int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scores_device, void* cuda_stream) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (model->device != db->device) return fail(MSV_ERR_INVALID_ARGUMENT, "model and database live on different devices");
+    if (db->n == 0) return MSV_OK;
+    if (!scores_device) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_device is NULL");
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const Viterbi_geometry* geo = model->geo;
+    msv::Scan_params p{};
+    p.table = model->d_table;
+    p.residues = db->d_residues;
+    p.offsets = db->d_offsets;
+    p.order = db->d_order;
+    p.length_tr = db->d_length_tr;
+    p.scores = scores_device;
+    p.queue_head = db->d_queue;
+    p.first_bad = db->d_first_bad;
+    p.n = static_cast<uint32_t>(db->n);
+    p.table_bytes = static_cast<uint32_t>(geo->shared_bytes());
+    p.tr_B_Mk = model->tr_B_Mk;
+    p.tr_E_C = model->tr_E_C;
+    p.tr_E_J = model->tr_E_J;
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, sizeof(unsigned int), stream));
+    // persistent CTAs, one per SM, one warp per sequence in flight; fewer warps when there are fewer sequences
+    const size_t warps_per_cta = static_cast<size_t>(geo->threads) / 32;
+    const size_t ctas = std::max<size_t>(1, std::min<size_t>(model->sm_count, (db->n + warps_per_cta - 1) / warps_per_cta));
+    const size_t warps = ctas == 1 ? std::min(warps_per_cta, db->n) : std::min(warps_per_cta, (db->n + ctas - 1) / ctas);
+    const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
+    (cj_same ? geo->fn_cj_same : geo->fn)<<<static_cast<int>(ctas), static_cast<int>(warps * 32), geo->shared_bytes(), stream>>>(p);
+    msv_detail::count_launch();
+    MSV_CUDA_TRY(cudaGetLastError());
+    return MSV_OK;
+}
+
+int msv_cuda_db_viterbi(msv_viterbi_model* model, msv_db* db, float* scores_host) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (db->n && !scores_host) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_host is NULL");
+    if (int rc = msv_cuda_db_viterbi_device(model, db, db->d_scores, nullptr)) return rc;
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    if (db->n) MSV_CUDA_TRY(cudaMemcpy(scores_host, db->d_scores, db->n * sizeof(float), cudaMemcpyDeviceToHost));
+    return MSV_OK;
+}
+
+int msv_cuda_viterbi_batch(msv_viterbi_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host) {
+    if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
+    if (n && (!offsets || !scores_host)) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
+    msv_db* db = nullptr;
+    if (int rc = msv_cuda_db_create(model->device, residues, offsets, n, &db)) return rc;
+    const int rc = msv_cuda_db_viterbi(model, db, scores_host);
+    msv_cuda_db_destroy(db);
+    return rc;
+}
+
+} // extern "C"

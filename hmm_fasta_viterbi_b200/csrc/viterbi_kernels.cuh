@@ -1,0 +1,238 @@
+// viterbi_kernels.cuh -- Plan-7 local multihit Viterbi scan for B200 (sm_100a): match, insert and delete states.
+//
+// This is SURVEY.md section 8(f) rank 4, the step the reference names as its direction (README.md:2-3) and for which it
+// parses `transitions` (data_readers/Profile_HMM.hpp:27-29) without using them.  Same database, same special states,
+// same emission table and same uniform local entry as the MSV path (reference algorithms/MSV_HMM.cpp:38-53,59-64,
+// 107-112); per cell (i = residue, k = model column):
+//     M[i][k] = e[x_i][k] + max(M[i-1][k-1] + tMM[k-1], I[i-1][k-1] + tIM[k-1], D[i-1][k-1] + tDM[k-1], B[i-1] + tBMk)
+//     I[i][k] = max(M[i-1][k] + tMI[k], I[i-1][k] + tII[k])                  (insert emissions score 0, as in HMMER3)
+//     D[i][k] = max(M[i][k-1] + tMD[k-1], D[i][k-1] + tDD[k-1])
+//     E[i]    = max(max_k M[i][k], D[i][LENG])
+// Every transcendental is evaluated on the host; the device only adds and takes maxima in fp32, each add on the same
+// two operands as the scalar evaluation (oracle/viterbi_oracle.c), so scores are bit-identical to it:
+//   * max is exact and order-free for the values that occur (finite and -inf), and rounding is monotone, so
+//     fl(max(a, b) + t) == max(fl(a + t), fl(b + t)): the delete chain may be evaluated as a maximum over paths as long
+//     as every path is summed left to right -- which is what the cross-lane propagation below does.
+//
+// Mapping.  One warp per sequence; lane l keeps K consecutive model columns of all three states in registers
+// (m[K], in[K], d[K]).  The model is RIGHT-aligned in the 32*K slots: slot s = l*K + j holds column s - (32K - 1 - LENG),
+// so the last real column is always the last slot of lane 31 (D[LENG] enters E with one predicated max) and slot 0 is
+// always a dummy (-inf emissions and transitions), which makes the rotating shuffles below need no select.
+//
+// Where the operands come from (per cell: 7 transitions + 1 emission = 32 B, more than shared memory alone can feed):
+//   * tensor memory, 5 words per column: tMM, tIM, tDM of the column to the left, tMI, tII of the column itself;
+//     laid out per lane in groups of 4 columns (20 words: one tcgen05.ld.x16 + one .x4), fetched one group ahead;
+//   * shared memory: the emission row of the residue (one LDS.128 per 4 columns) and tMD, tDD of the column to the left
+//     (two LDS.128 per 4 columns), staged once per CTA by the TMA unit.
+//
+// The delete chain is serial in k.  Each lane first runs its own K columns with an incoming D of -inf; then the carried-in
+// path D[left lane's last column] + tDD + tDD + ... is pushed through the lane, four columns at a time, for as long as it
+// still improves some column in some lane (it loses ~1 nat per column against the local alternatives, so it normally dies
+// within the first group), and the whole step is repeated only if a carried-in path crossed an entire lane.
+#pragma once
+
+#include "msv_device.cuh"
+
+namespace msv {
+
+constexpr int kViterbiMaxColumnsPerLane = 80; // 22 * K * 128 B of shared memory
+
+// Table in global memory (floats), K columns per lane, Q = K / 4:
+//   [0, 20*K*32)                  emissions             [residue][q][lane][4]
+//   [.., + K*32)                  tMD of the left column [q][lane][4]
+//   [.., + K*32)                  tDD of the left column [q][lane][4]          <- end of the shared-memory part
+//   [.., + 32*5*K)                tensor-memory part     [lane][q][tMM x4 | tIM x4 | tDM x4 | tMI x4 | tII x4]
+//   [.., + 32*4)                  per lane: tMM, tIM, tDM of the column left of the NEXT lane's first slot, tDD left of
+//                                 this lane's first slot
+template <int K, int THREADS, bool CJ_SAME>
+__global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Scan_params p) {
+    static_assert(K % 4 == 0 && K >= 4 && K <= kViterbiMaxColumnsPerLane, "columns per lane");
+    constexpr int Q = K / 4;
+    constexpr uint32_t ROW_BYTES = K * 32 * 4; // one residue's emissions; also the size of the tMD and of the tDD block
+    constexpr uint32_t EMISSION_BYTES = kAlphabet * ROW_BYTES;
+    constexpr uint32_t SMEM_TABLE_BYTES = EMISSION_BYTES + 2 * ROW_BYTES;
+    constexpr uint32_t TENSOR_WORDS = 5 * K; // per lane
+    constexpr uint32_t COPY_CHUNK = 32768;
+    constexpr uint32_t TMEM_COLUMNS = 512;
+    static_assert(TENSOR_WORDS <= TMEM_COLUMNS, "transitions of one lane must fit its tensor-memory lane");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t table_ready;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    if (p.first_bad != nullptr && *p.first_bad != ~0ull) return; // never index the table with an unvalidated residue code
+
+    if (threadIdx.x == 0) mbarrier_init(&table_ready, 1);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "n"(TMEM_COLUMNS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (threadIdx.x == 0) {
+        mbarrier_expect_tx(&table_ready, SMEM_TABLE_BYTES);
+#pragma unroll 1
+        for (uint32_t at = 0; at < SMEM_TABLE_BYTES; at += COPY_CHUNK) {
+            const uint32_t bytes = min(COPY_CHUNK, SMEM_TABLE_BYTES - at);
+            tma_bulk_load(smem_raw + at, reinterpret_cast<const unsigned char*>(p.table) + at, bytes, &table_ready);
+        }
+    }
+    const float* tensor_src = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p.table) + SMEM_TABLE_BYTES);
+    const uint32_t tmem_lane_base = tmem_base_slot + ((static_cast<uint32_t>(warp & 3) * 32u) << 16);
+    if (warp < 4) { // each of the first four warps writes the copy of its own lane quarter
+        const float2* src = reinterpret_cast<const float2*>(tensor_src + static_cast<size_t>(lane) * TENSOR_WORDS);
+#pragma unroll 4
+        for (uint32_t w = 0; w < TENSOR_WORDS / 2; ++w) {
+            const float2 a = __ldg(src + w);
+            tmem_store2(tmem_lane_base + 2 * w, a.x, a.y);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mbarrier_wait(&table_ready, 0);
+
+    const float4 edge = __ldg(reinterpret_cast<const float4*>(tensor_src + 32 * TENSOR_WORDS) + lane);
+    const uint32_t tab_lane = smem_u32(smem_raw) + lane * 16;
+    const uint32_t md_lane = tab_lane + EMISSION_BYTES, dd_lane = md_lane + ROW_BYTES;
+    const int left_lane = (lane + 31) & 31;
+    const float NEG_INF = __int_as_float(0xff800000);
+    const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
+
+    for (;;) {
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(p.queue_head, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= p.n) break;
+        const uint32_t idx = __ldg(p.order + ticket);
+        const uint64_t begin = __ldg(p.offsets + idx);
+        const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
+        const float2 tr = __ldg(p.length_tr + len);
+        const float loop = tr.x, move = tr.y;
+
+        float m[K], in[K], d[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) m[j] = in[j] = d[j] = NEG_INF;
+        float J = NEG_INF, C = NEG_INF, N = 0.0f, B = move;
+
+        // transitions of the column group at hand / of the next one (tensor memory, double buffered across the unrolled loop)
+        float tq[2][20];
+        tmem_load<20>(tmem_lane_base + (Q - 1) * 20, tq[(Q - 1) & 1]);
+
+        auto row = [&](const uint32_t x) {
+            const uint32_t erow = tab_lane + x * ROW_BYTES;
+            const float bt = B + tBMk;
+            // what the first column of the lane to the right receives from this lane's last column (previous row);
+            // lane 31's `edge` is -inf, so lane 0 receives -inf: nothing enters the model's left end
+            const float out = fmaxf(fmaxf(m[K - 1] + edge.x, in[K - 1] + edge.y), d[K - 1] + edge.z);
+            const float left = __shfl_sync(0xffffffffu, out, left_lane);
+            float e = NEG_INF;
+            // ---- match and insert states, highest column first so that [j-1] is still the previous row ----
+#pragma unroll
+            for (int q = Q - 1; q >= 0; --q) {
+                float* t = tq[q & 1];
+                tmem_wait<20>(t);
+                if (q > 0) tmem_load<20>(tmem_lane_base + (q - 1) * 20, tq[(q - 1) & 1]);
+                const float4 ev = lds128(erow + q * 512);
+                const float em[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+                for (int c = 3; c >= 0; --c) {
+                    const int j = 4 * q + c;
+                    const float ins = fmaxf(m[j] + t[12 + c], in[j] + t[16 + c]);
+                    float from_left;
+                    if (j > 0) {
+                        const int jl = j > 0 ? j - 1 : 0;
+                        from_left = fmaxf(fmaxf(m[jl] + t[c], in[jl] + t[4 + c]), d[jl] + t[8 + c]);
+                    } else {
+                        from_left = left;
+                    }
+                    m[j] = em[c] + fmaxf(from_left, bt);
+                    in[j] = ins;
+                    e = fmaxf(e, m[j]);
+                }
+                // after the lowest group: request the highest group for the next row (it lands during the delete pass);
+                // issued after the group's arithmetic because for odd Q both use the same registers
+                if (q == 0) tmem_load<20>(tmem_lane_base + (Q - 1) * 20, tq[(Q - 1) & 1]);
+            }
+            // ---- delete states: own columns first (carried-in D = -inf) ----
+            const float m_left = __shfl_sync(0xffffffffu, m[K - 1], left_lane); // lane 0: its slot 0 is a dummy, tMD = -inf
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float4 md = lds128(md_lane + q * 512), dd = lds128(dd_lane + q * 512);
+                const int j = 4 * q;
+                d[j] = q == 0 ? m_left + md.x : fmaxf(m[j > 0 ? j - 1 : 0] + md.x, d[j > 0 ? j - 1 : 0] + dd.x);
+                d[j + 1] = fmaxf(m[j] + md.y, d[j] + dd.y);
+                d[j + 2] = fmaxf(m[j + 1] + md.z, d[j + 1] + dd.z);
+                d[j + 3] = fmaxf(m[j + 2] + md.w, d[j + 2] + dd.w);
+            }
+            // ---- then the paths that arrive from the lane to the left ----
+            for (;;) {
+                const float d_left = __shfl_sync(0xffffffffu, d[K - 1], left_lane);
+                float carried = d_left + edge.w; // edge.w = tDD left of this lane's first slot (-inf for lane 0)
+                if (!__any_sync(0xffffffffu, carried > d[0])) break;
+                bool crossed = true; // a carried path is still alive after the last column of some lane
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const int j = 4 * q;
+                    const float4 dd = lds128(dd_lane + q * 512);
+                    if (q > 0) {
+                        carried = carried + dd.x;
+                        if (!__any_sync(0xffffffffu, carried > d[j])) { // dead everywhere: nothing further can change
+                            crossed = false;
+                            break;
+                        }
+                    }
+                    d[j] = fmaxf(d[j], carried);
+                    carried = carried + dd.y;
+                    d[j + 1] = fmaxf(d[j + 1], carried);
+                    carried = carried + dd.z;
+                    d[j + 2] = fmaxf(d[j + 2], carried);
+                    carried = carried + dd.w;
+                    d[j + 3] = fmaxf(d[j + 3], carried);
+                }
+                if (!crossed) break;
+            }
+            if (lane == 31) e = fmaxf(e, d[K - 1]); // D[LENG] -> E
+            float E;
+            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(E) : "f"(e));
+            J = fmaxf(J + loop, E + tEJ);
+            if constexpr (!CJ_SAME) C = fmaxf(C + loop, E + tEC);
+            N = N + loop;
+            B = fmaxf(N, J) + move;
+        };
+
+        // residues arrive as aligned 32-bit words; a funnel shift undoes the byte misalignment of the sequence start
+        const uint32_t shift = (static_cast<uint32_t>(begin) & 3u) * 8u;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues + (begin & ~static_cast<uint64_t>(3)));
+        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        wp += 2;
+        uint32_t word = __funnelshift_r(w0, w1, shift);
+#pragma unroll 1
+        for (uint32_t i = 0; i < len; ++i) {
+            row(word & 0xffu);
+            word >>= 8;
+            if ((i & 3u) == 3u) {
+                w0 = w1;
+                w1 = __ldg(wp);
+                ++wp;
+                word = __funnelshift_r(w0, w1, shift);
+            }
+        }
+        tmem_wait<20>(tq[(Q - 1) & 1]); // retire the group that was requested for a row that does not exist
+        if (lane == 0) p.scores[idx] = (CJ_SAME ? J : C) + move;
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_slot), "n"(TMEM_COLUMNS) : "memory");
+}
+
+} // namespace msv

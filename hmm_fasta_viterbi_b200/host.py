@@ -73,6 +73,12 @@ lib.msvh_device_database_create.restype = _vp
 lib.msvh_device_database_create.argtypes = [_vp, C.c_int]
 lib.msvh_device_database_free.argtypes = [_vp]
 lib.msvh_msv_parallel_run_on_device_database.argtypes = [_vp, _vp, _f32]
+lib.msvh_viterbi_create.restype = _vp
+lib.msvh_viterbi_create.argtypes = [_vp, C.c_int]
+lib.msvh_viterbi_free.argtypes = [_vp]
+lib.msvh_viterbi_parallel_run_on_sequence.argtypes = [_vp, C.c_char_p, C.POINTER(C.c_float)]
+lib.msvh_viterbi_parallel_run_on_packed.argtypes = [_vp, _vp, _f32]
+lib.msvh_viterbi_parallel_run_on_device_database.argtypes = [_vp, _vp, _f32]
 lib.msvh_msv_filter.restype = C.c_long
 lib.msvh_msv_filter.argtypes = [_vp, _vp, C.c_float, C.c_size_t, _vp, _vp, _vp, _vp]
 lib.msvh_msv_parallel_run_on_packed_devices.argtypes = [_vp, _vp, C.POINTER(C.c_int), C.c_int, _f32]
@@ -259,4 +265,37 @@ class MSV_HMM:
     def __del__(self) -> None:
         if getattr(self, "_h", None):
             lib.msvh_msv_free(self._h)
+            self._h = None
+
+
+class Viterbi_HMM:
+    """algorithms/Viterbi_HMM.hpp: Plan-7 local Viterbi (match/insert/delete) with MSV_HMM's calling conventions."""
+
+    def __init__(self, base_hmm: Profile_HMM, device: int = 0) -> None:
+        self._h = lib.msvh_viterbi_create(base_hmm._h, device)
+        if not self._h:
+            _raise(-1)
+
+    def parallel_run_on_sequence(self, seq: str) -> np.float32:
+        out = C.c_float()
+        status = lib.msvh_viterbi_parallel_run_on_sequence(self._h, seq.encode("latin-1"), C.byref(out))
+        if status:
+            _raise(status)
+        return np.float32(out.value)
+
+    def parallel_run_on_sequences(self, database) -> np.ndarray:
+        if isinstance(database, FASTA_protein_sequences):
+            database = Packed_sequences.from_fasta(database)
+        out = np.empty(max(len(database), 1), np.float32)
+        if isinstance(database, Device_database):
+            status = lib.msvh_viterbi_parallel_run_on_device_database(self._h, database._h, out)
+        else:
+            status = lib.msvh_viterbi_parallel_run_on_packed(self._h, database._h, out)
+        if status:
+            _raise(status)
+        return out[: len(database)]
+
+    def __del__(self) -> None:
+        if getattr(self, "_h", None):
+            lib.msvh_viterbi_free(self._h)
             self._h = None

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "MSV_HMM.hpp"
+#include "Viterbi_HMM.hpp"
 #include "Synthetic_database.hpp"
 #include "msv_cuda.h"
 
@@ -161,6 +162,32 @@ int msvh_msv_parallel_run_on_packed_devices(void* m, void* packed, const int* de
     return guarded([&] {
         const auto got = static_cast<MSV_HMM*>(m)->parallel_run_on_sequences(*static_cast<Packed_sequences*>(packed),
                                                                              std::vector<int>(devices, devices + n_devices));
+        if (!got.empty()) std::memcpy(scores, got.data(), got.size() * sizeof(float));
+    });
+}
+
+// ---- Viterbi_HMM ----
+void* msvh_viterbi_create(void* profile, int device) {
+    Viterbi_HMM* m = nullptr;
+    guarded([&] {
+        m = new Viterbi_HMM(*static_cast<Profile_HMM*>(profile));
+        m->set_device(device);
+    });
+    return m;
+}
+void msvh_viterbi_free(void* m) { delete static_cast<Viterbi_HMM*>(m); }
+int msvh_viterbi_parallel_run_on_sequence(void* m, const char* seq, float* score) {
+    return guarded([&] { *score = static_cast<Viterbi_HMM*>(m)->parallel_run_on_sequence(seq); });
+}
+int msvh_viterbi_parallel_run_on_packed(void* m, void* packed, float* scores) {
+    return guarded([&] {
+        const auto got = static_cast<Viterbi_HMM*>(m)->parallel_run_on_sequences(*static_cast<Packed_sequences*>(packed));
+        if (!got.empty()) std::memcpy(scores, got.data(), got.size() * sizeof(float));
+    });
+}
+int msvh_viterbi_parallel_run_on_device_database(void* m, void* d, float* scores) {
+    return guarded([&] {
+        const auto got = static_cast<Viterbi_HMM*>(m)->parallel_run_on_sequences(*static_cast<Device_database*>(d));
         if (!got.empty()) std::memcpy(scores, got.data(), got.size() * sizeof(float));
     });
 }

@@ -30,8 +30,9 @@
 extern "C" {
 #endif
 
-#define MSV_CUDA_ABI_VERSION 1
+#define MSV_CUDA_ABI_VERSION 2
 #define MSV_ALPHABET 20
+#define MSV_TRANSITIONS 7 /* m->m m->i m->d i->m i->i d->m d->d, the order of Profile_HMM::transitions (Profile_HMM.hpp:29) */
 
 enum {
     MSV_OK = 0,
@@ -141,6 +142,39 @@ int msv_cuda_db_score_filter(msv_model* model, msv_db* db, float mu, float lambd
  * fraction of the link speed).  Registration is expensive (of the order of 1 ms per 4 MB): do it once per database. */
 int msv_cuda_host_register(const void* buffer, size_t bytes);
 int msv_cuda_host_unregister(const void* buffer);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Plan-7 local multihit Viterbi scan: match, insert AND delete states over the node transitions that the reference
+ * parses (Profile_HMM::transitions, data_readers/Profile_HMM.hpp:27-29, Profile_HMM.cpp:105-121) and never uses -- the
+ * direction its README.md:2-3 names.  The reference has no implementation to be bit-compatible with; the recurrence is
+ * the published one (HMMER3's generic Viterbi) in the conventions of the reference's MSV path, so both scans see one
+ * model: same emission table, uniform local entry tr_B_Mk, free local exit M_k -> E and D_LENG -> E, tr_E_C / tr_E_J,
+ * length-dependent loop / move scores; insert emissions score 0 as in HMMER3's profile configuration.
+ *     M[i][k] = e[x_i][k] + max(M[i-1][k-1] + tMM[k-1], I[i-1][k-1] + tIM[k-1], D[i-1][k-1] + tDM[k-1], B[i-1] + tr_B_Mk)
+ *     I[i][k] = max(M[i-1][k] + tMI[k], I[i-1][k] + tII[k])            k < LENG
+ *     D[i][k] = max(M[i][k-1] + tMD[k-1], D[i][k-1] + tDD[k-1])        k >= 2
+ *     E[i]    = max(max_k M[i][k], D[i][LENG]);   J, C, N, B and the score as in the MSV path (MSV_HMM.cpp:107-112)
+ * fp32 throughout, adds and maxima only on the device; scores are bit-identical to the scalar evaluation of these
+ * equations (oracle/viterbi_oracle.c).  Models up to 32 x 80 - 1 = 2559 columns.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct msv_viterbi_model msv_viterbi_model;
+
+/* log_transitions[node * 7 + t] = logf(transitions[node * 7 + t]) for node = 0 .. model_length - 1 (probabilities as
+ * Profile_HMM stores them, including its '*' -> 1.0 quirk, Profile_HMM.cpp:40; rows 0 and LENG are never read). */
+int msv_host_viterbi_transitions(const float* transitions, size_t model_length, float* log_transitions);
+/* emission_scores as for msv_cuda_model_create; log_transitions [model_length][7], every value <= 0 (-inf allowed). */
+int msv_cuda_viterbi_model_create(const float* emission_scores, const float* log_transitions, size_t model_length, float tr_B_Mk,
+                                  float tr_E_C, float tr_E_J, int device, msv_viterbi_model** out);
+int msv_cuda_viterbi_model_destroy(msv_viterbi_model* model);
+/* one warp per sequence: model columns per lane, threads per CTA, dynamic shared memory bytes.  Any pointer may be NULL. */
+int msv_cuda_viterbi_model_geometry(const msv_viterbi_model* model, int* columns_per_lane, int* threads_per_cta, size_t* shared_bytes);
+/* resident database (the same msv_db the MSV scan uses), one launch; scores_device: DEVICE pointer to n floats in
+ * original sequence order; asynchronous on `cuda_stream`. */
+int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scores_device, void* cuda_stream);
+/* resident database, host result (synchronous). */
+int msv_cuda_db_viterbi(msv_viterbi_model* model, msv_db* db, float* scores_host);
+/* HOST buffers in and out: upload + bucket + scan + download in one synchronous call. */
+int msv_cuda_viterbi_batch(msv_viterbi_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host);
 
 /* kernel launches issued by this library on the calling thread since the last reset (for bench.py's gpu_launches) */
 uint64_t msv_cuda_launch_count(int reset);

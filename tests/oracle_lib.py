@@ -80,6 +80,10 @@ class Oracle:
         L.oracle_msv_score_string.restype = C.c_int
         L.oracle_msv_score_string.argtypes = [_f32p, C.c_size_t, _f32p, C.c_char_p, C.POINTER(C.c_float)]
         L.oracle_msv_score_batch.argtypes = [_f32p, C.c_size_t, _f32p, _u8p, _u64p, C.c_size_t, _f32p, C.c_int]
+        L.oracle_viterbi_prepare.argtypes = [_f32p, C.c_size_t, _f32p]
+        L.oracle_viterbi_score_codes.restype = C.c_float
+        L.oracle_viterbi_score_codes.argtypes = [_f32p, _f32p, C.c_size_t, _f32p, _u8p, C.c_size_t, C.c_void_p]
+        L.oracle_viterbi_score_batch.argtypes = [_f32p, _f32p, C.c_size_t, _f32p, _u8p, _u64p, C.c_size_t, _f32p, C.c_int]
 
     # ---- readers ----
     def load_hmm(self, path: str) -> dict:
@@ -146,6 +150,31 @@ class Oracle:
             codes = np.zeros(1, np.uint8)
         self.lib.oracle_msv_score_batch(table, table.shape[1], tr3, codes, np.ascontiguousarray(offsets, np.uint64), n, out,
                                         threads)
+        return out
+
+    # ---- Plan-7 local Viterbi (oracle/viterbi_oracle.c; parity unpinned, see its header) ----
+    def viterbi_prepare(self, transitions: np.ndarray) -> np.ndarray:
+        t = np.ascontiguousarray(transitions, np.float32)
+        out = np.empty_like(t)
+        self.lib.oracle_viterbi_prepare(t, t.shape[0], out)
+        return out
+
+    def viterbi_score_codes(self, table, logtr, tr3, codes) -> np.float32:
+        codes = np.ascontiguousarray(codes, np.uint8)
+        n = codes.size
+        if n == 0:
+            codes = np.zeros(1, np.uint8)
+        return np.float32(self.lib.oracle_viterbi_score_codes(table, np.ascontiguousarray(logtr, np.float32), table.shape[1], tr3,
+                                                              codes, n, None))
+
+    def viterbi_score_batch(self, table, logtr, tr3, codes, offsets, threads: int = 1) -> np.ndarray:
+        n = len(offsets) - 1
+        out = np.empty(n, dtype=np.float32)
+        codes = np.ascontiguousarray(codes, np.uint8)
+        if codes.size == 0:
+            codes = np.zeros(1, np.uint8)
+        self.lib.oracle_viterbi_score_batch(table, np.ascontiguousarray(logtr, np.float32), table.shape[1], tr3, codes,
+                                            np.ascontiguousarray(offsets, np.uint64), n, out, threads)
         return out
 
 

@@ -35,7 +35,7 @@ def test_cabi_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
     assert declared <= exported
-    assert _cabi.lib.msv_cuda_abi_version() == 1
+    assert _cabi.lib.msv_cuda_abi_version() == 2
 
 
 def test_cabi_has_no_torch_or_oracle_dependency():
@@ -66,6 +66,20 @@ def test_gpu_entry_points_fail_loudly_without_a_device(oracle):
     model = msv.MSV_HMM(msv.Profile_HMM(hmm_path("100.hmm")))
     with pytest.raises(RuntimeError, match="no CUDA device"):
         model.parallel_run_on_sequence("#ACDEF")
+    # the Viterbi scan has no host implementation either
+    with pytest.raises(_cabi.MsvCudaError) as err:
+        msv.ViterbiModel(table, _cabi.viterbi_transitions(h["transitions"]), *_cabi.model_transitions(h["model_length"]))
+    assert err.value.status == _cabi.MSV_ERR_NO_DEVICE
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        msv.Viterbi_HMM(msv.Profile_HMM(hmm_path("100.hmm"))).parallel_run_on_sequence("#ACDEF")
+
+
+def test_viterbi_host_transitions_match_oracle(oracle):
+    for name in ("100.hmm", "2405.hmm"):
+        h = oracle.load_hmm(hmm_path(name))
+        mine, theirs = _cabi.viterbi_transitions(h["transitions"]), oracle.viterbi_prepare(h["transitions"])
+        assert mine.view(np.uint32).tolist() == theirs.view(np.uint32).tolist()
+        assert np.all(mine <= 0)
 
 
 # ---- host helpers vs oracle -------------------------------------------------------------------------------------
