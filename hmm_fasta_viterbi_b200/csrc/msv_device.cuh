@@ -79,6 +79,13 @@ __device__ __forceinline__ float4 lds128(uint32_t shared_address) {
     return v;
 }
 
+// same, but never hoisted out of a loop or merged: for loop-invariant tables that must NOT be promoted to registers
+__device__ __forceinline__ float4 lds128_volatile(uint32_t shared_address) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(shared_address));
+    return v;
+}
+
 // ---- tensor memory (TMEM) accessors: tcgen05.ld/st.32x32b.xN gives thread t of a warp N consecutive 32-bit columns of
 // TMEM lane 32*(warp%4)+t ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_load8(uint32_t taddr, float* v) {

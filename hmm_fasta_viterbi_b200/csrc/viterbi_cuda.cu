@@ -18,7 +18,7 @@ struct Viterbi_geometry {
     int K, threads;
     Scan_kernel fn, fn_cj_same;
     size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 * sizeof(float); }
-    size_t table_floats() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 + 32 * 5 * static_cast<size_t>(K) + 32 * 4; }
+    size_t table_floats() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 + 32 * 5 * static_cast<size_t>(K) + 32 * 8; }
 };
 
 // three state registers per column: the register file, not shared memory, bounds the warps per SM
@@ -94,11 +94,8 @@ int msv_cuda_viterbi_model_create(const float* emission_scores, const float* log
     const float ninf = -std::numeric_limits<float>::infinity();
     enum { MM = 0, MI = 1, MD = 2, IM = 3, II = 4, DM = 5, DD = 6 }; // order of Profile_HMM::transitions (Profile_HMM.hpp:29)
     const auto tr = [&](long node, int which) { return log_transitions[node * MSV_TRANSITIONS + which]; };
-    const auto from_left = [&](long slot, int which) { // transition `which` of the column left of `slot`, into `slot`
-        const long c = slot - pad;
-        return (c >= 2 && c <= columns) ? tr(c - 1, which) : ninf;
-    };
-    const auto own = [&](long slot, int which) { // insert-state transitions of the column in `slot` (there is no I_LENG)
+    // every transition is stored with the column it leaves; columns 1 .. LENG-1 have successors, nothing else does
+    const auto own = [&](long slot, int which) {
         const long c = slot - pad;
         return (c >= 1 && c <= columns - 1) ? tr(c, which) : ninf;
     };
@@ -115,20 +112,18 @@ int msv_cuda_viterbi_model_create(const float* emission_scores, const float* log
             const size_t at = (static_cast<size_t>(q) * 32 + lane) * 4 + w;
             for (int res = 0; res < MSV_ALPHABET; ++res)
                 laid[res * row + at] = (c >= 1 && c <= columns) ? emission_scores[res * model_length + c] : ninf;
-            md[at] = from_left(slot, MD);
-            dd[at] = from_left(slot, DD);
+            md[at] = own(slot, MD);
+            dd[at] = own(slot, DD);
             float* t = tensor + (static_cast<size_t>(lane) * (K / 4) + q) * 20;
-            t[w] = from_left(slot, MM);
-            t[4 + w] = from_left(slot, IM);
-            t[8 + w] = from_left(slot, DM);
+            t[w] = own(slot, MM);
+            t[4 + w] = own(slot, IM);
+            t[8 + w] = own(slot, DM);
             t[12 + w] = own(slot, MI);
             t[16 + w] = own(slot, II);
         }
-        const long next = static_cast<long>(lane + 1) * K;
-        edge[lane * 4 + 0] = lane < 31 ? from_left(next, MM) : ninf;
-        edge[lane * 4 + 1] = lane < 31 ? from_left(next, IM) : ninf;
-        edge[lane * 4 + 2] = lane < 31 ? from_left(next, DM) : ninf;
-        edge[lane * 4 + 3] = from_left(static_cast<long>(lane) * K, DD);
+        const long last = static_cast<long>(lane) * K + K - 1; // lane 31: column LENG, which has no successor
+        const int which[5] = {MM, IM, DM, MD, DD};
+        for (int i = 0; i < 5; ++i) edge[lane * 8 + i] = own(last, which[i]);
     }
 
     auto* model = new (std::nothrow) msv_viterbi_model();

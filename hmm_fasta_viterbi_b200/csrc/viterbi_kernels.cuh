@@ -19,16 +19,25 @@
 // so the last real column is always the last slot of lane 31 (D[LENG] enters E with one predicated max) and slot 0 is
 // always a dummy (-inf emissions and transitions), which makes the rotating shuffles below need no select.
 //
-// Where the operands come from (per cell: 7 transitions + 1 emission = 32 B, more than shared memory alone can feed):
-//   * tensor memory, 5 words per column: tMM, tIM, tDM of the column to the left, tMI, tII of the column itself;
-//     laid out per lane in groups of 4 columns (20 words: one tcgen05.ld.x16 + one .x4), fetched one group ahead;
-//   * shared memory: the emission row of the residue (one LDS.128 per 4 columns) and tMD, tDD of the column to the left
-//     (two LDS.128 per 4 columns), staged once per CTA by the TMA unit.
+// One ASCENDING pass per row does all three states of a column together.  Every transition is stored with the column it
+// LEAVES ("outgoing"), so column j first turns its previous-row states into what column j+1 will receive,
+//     a[j] = max(m[j] + tMM[j], in[j] + tIM[j], d[j] + tDM[j]),
+// and only then overwrites them with the new row: m[j] = e + max(a[j-1], B + tBMk), in[j] from the old m[j], in[j], and
+// d[j] = max(m_new[j-1] + tMD[j-1], d_new[j-1] + tDD[j-1]).  The serial delete chain therefore runs one column behind the
+// match/insert arithmetic of the same pass, whose independent instructions hide its latency.
 //
-// The delete chain is serial in k.  Each lane first runs its own K columns with an incoming D of -inf; then the carried-in
-// path D[left lane's last column] + tDD + tDD + ... is pushed through the lane, four columns at a time, for as long as it
-// still improves some column in some lane (it loses ~1 nat per column against the local alternatives, so it normally dies
-// within the first group), and the whole step is repeated only if a carried-in path crossed an entire lane.
+// Across lanes: the lane to the left hands over a[K-1] (previous row; one shuffle at the top of the row) and, after the
+// pass, c = max(m_new[K-1] + tMD[K-1], d_new[K-1] + tDD[K-1]), the value of D in this lane's first slot.  Each lane has run
+// its own chain with d[0] = -inf; the carried-in path c, c + tDD[0], c + tDD[0] + tDD[1], ... is then pushed through the
+// lane four columns at a time for as long as it still improves some column in some lane (it loses ~1 nat per column
+// against the local alternatives, so it normally dies within the first group), and the hand-over is repeated only if a
+// carried-in path crossed an entire lane.  Every path is summed left to right, as the scalar evaluation does.
+//
+// Where the operands come from (per cell: 7 transitions + 1 emission = 32 B, more than shared memory alone can feed):
+//   * tensor memory, 5 words per column (tMM, tIM, tDM, tMI, tII), laid out per lane in groups of 4 columns (20 words:
+//     one tcgen05.ld.x16 + one .x4), fetched one group ahead;
+//   * shared memory: the emission row of the residue (one LDS.128 per 4 columns) and tMD, tDD (two LDS.128 per 4
+//     columns), staged once per CTA by the TMA unit.
 #pragma once
 
 #include "msv_device.cuh"
@@ -37,13 +46,13 @@ namespace msv {
 
 constexpr int kViterbiMaxColumnsPerLane = 80; // 22 * K * 128 B of shared memory
 
-// Table in global memory (floats), K columns per lane, Q = K / 4:
-//   [0, 20*K*32)                  emissions             [residue][q][lane][4]
-//   [.., + K*32)                  tMD of the left column [q][lane][4]
-//   [.., + K*32)                  tDD of the left column [q][lane][4]          <- end of the shared-memory part
+// Table in global memory (floats), K columns per lane, Q = K / 4; every transition belongs to the column it leaves:
+//   [0, 20*K*32)                  emissions              [residue][q][lane][4]
+//   [.., + K*32)                  tMD                    [q][lane][4]
+//   [.., + K*32)                  tDD                    [q][lane][4]          <- end of the shared-memory part
 //   [.., + 32*5*K)                tensor-memory part     [lane][q][tMM x4 | tIM x4 | tDM x4 | tMI x4 | tII x4]
-//   [.., + 32*4)                  per lane: tMM, tIM, tDM of the column left of the NEXT lane's first slot, tDD left of
-//                                 this lane's first slot
+//   [.., + 32*8)                  per lane: tMM, tIM, tDM, tMD, tDD of the lane's LAST slot (what it hands to the right; -inf
+//                                 for lane 31), 3 unused words
 template <int K, int THREADS, bool CJ_SAME>
 __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Scan_params p) {
     static_assert(K % 4 == 0 && K >= 4 && K <= kViterbiMaxColumnsPerLane, "columns per lane");
@@ -99,7 +108,8 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     mbarrier_wait(&table_ready, 0);
 
-    const float4 edge = __ldg(reinterpret_cast<const float4*>(tensor_src + 32 * TENSOR_WORDS) + lane);
+    const float4 edge = __ldg(reinterpret_cast<const float4*>(tensor_src + 32 * TENSOR_WORDS) + 2 * lane);
+    const float edge_dd = __ldg(tensor_src + 32 * TENSOR_WORDS + 8 * lane + 4);
     const uint32_t tab_lane = smem_u32(smem_raw) + lane * 16;
     const uint32_t md_lane = tab_lane + EMISSION_BYTES, dd_lane = md_lane + ROW_BYTES;
     const int left_lane = (lane + 31) & 31;
@@ -124,78 +134,67 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
 
         // transitions of the column group at hand / of the next one (tensor memory, double buffered across the unrolled loop)
         float tq[2][20];
-        tmem_load<20>(tmem_lane_base + (Q - 1) * 20, tq[(Q - 1) & 1]);
+        tmem_load<20>(tmem_lane_base, tq[0]);
 
         auto row = [&](const uint32_t x) {
             const uint32_t erow = tab_lane + x * ROW_BYTES;
             const float bt = B + tBMk;
-            // what the first column of the lane to the right receives from this lane's last column (previous row);
-            // lane 31's `edge` is -inf, so lane 0 receives -inf: nothing enters the model's left end
-            const float out = fmaxf(fmaxf(m[K - 1] + edge.x, in[K - 1] + edge.y), d[K - 1] + edge.z);
-            const float left = __shfl_sync(0xffffffffu, out, left_lane);
+            // what the first slot of the lane to the right receives from this lane's last slot (previous row); lane 31's
+            // edge transitions are -inf, so lane 0 receives -inf: nothing enters the model's left end
+            const float a_last = fmaxf(fmaxf(m[K - 1] + edge.x, in[K - 1] + edge.y), d[K - 1] + edge.z);
+            float a_prev = __shfl_sync(0xffffffffu, a_last, left_lane);
             float e = NEG_INF;
-            // ---- match and insert states, highest column first so that [j-1] is still the previous row ----
-#pragma unroll
-            for (int q = Q - 1; q >= 0; --q) {
-                float* t = tq[q & 1];
-                tmem_wait<20>(t);
-                if (q > 0) tmem_load<20>(tmem_lane_base + (q - 1) * 20, tq[(q - 1) & 1]);
-                const float4 ev = lds128(erow + q * 512);
-                const float em[4] = {ev.x, ev.y, ev.z, ev.w};
-#pragma unroll
-                for (int c = 3; c >= 0; --c) {
-                    const int j = 4 * q + c;
-                    const float ins = fmaxf(m[j] + t[12 + c], in[j] + t[16 + c]);
-                    float from_left;
-                    if (j > 0) {
-                        const int jl = j > 0 ? j - 1 : 0;
-                        from_left = fmaxf(fmaxf(m[jl] + t[c], in[jl] + t[4 + c]), d[jl] + t[8 + c]);
-                    } else {
-                        from_left = left;
-                    }
-                    m[j] = em[c] + fmaxf(from_left, bt);
-                    in[j] = ins;
-                    e = fmaxf(e, m[j]);
-                }
-                // after the lowest group: request the highest group for the next row (it lands during the delete pass);
-                // issued after the group's arithmetic because for odd Q both use the same registers
-                if (q == 0) tmem_load<20>(tmem_lane_base + (Q - 1) * 20, tq[(Q - 1) & 1]);
-            }
-            // ---- delete states: own columns first (carried-in D = -inf) ----
-            const float m_left = __shfl_sync(0xffffffffu, m[K - 1], left_lane); // lane 0: its slot 0 is a dummy, tMD = -inf
+            float md_prev = NEG_INF, dd_prev = NEG_INF; // tMD, tDD of the column one to the left (none for the lane's first slot)
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const float4 md = lds128(md_lane + q * 512), dd = lds128(dd_lane + q * 512);
-                const int j = 4 * q;
-                d[j] = q == 0 ? m_left + md.x : fmaxf(m[j > 0 ? j - 1 : 0] + md.x, d[j > 0 ? j - 1 : 0] + dd.x);
-                d[j + 1] = fmaxf(m[j] + md.y, d[j] + dd.y);
-                d[j + 2] = fmaxf(m[j + 1] + md.z, d[j + 1] + dd.z);
-                d[j + 3] = fmaxf(m[j + 2] + md.w, d[j + 2] + dd.w);
+                float* t = tq[q & 1];
+                tmem_wait<20>(t);
+                if (q + 1 < Q) tmem_load<20>(tmem_lane_base + (q + 1) * 20, tq[(q + 1) & 1]);
+                const float4 ev = lds128(erow + q * 512);
+                const float4 md4 = lds128_volatile(md_lane + q * 512), dd4 = lds128_volatile(dd_lane + q * 512);
+                const float em[4] = {ev.x, ev.y, ev.z, ev.w}, md[4] = {md4.x, md4.y, md4.z, md4.w}, dd[4] = {dd4.x, dd4.y, dd4.z, dd4.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = 4 * q + c;
+                    const float a = j == K - 1 ? a_last : fmaxf(fmaxf(m[j] + t[c], in[j] + t[4 + c]), d[j] + t[8 + c]);
+                    const float ins = fmaxf(m[j] + t[12 + c], in[j] + t[16 + c]);
+                    const float m_new = em[c] + fmaxf(a_prev, bt);
+                    d[j] = j == 0 ? NEG_INF : fmaxf(m[j > 0 ? j - 1 : 0] + md_prev, d[j > 0 ? j - 1 : 0] + dd_prev); // m[j-1], d[j-1]: new row
+                    m[j] = m_new;
+                    in[j] = ins;
+                    e = fmaxf(e, m_new);
+                    a_prev = a;
+                    md_prev = md[c];
+                    dd_prev = dd[c];
+                }
+                // after the highest group: request the lowest group for the next row; issued after the group's arithmetic
+                // because for odd Q both use the same registers
+                if (q == Q - 1) tmem_load<20>(tmem_lane_base, tq[0]);
             }
-            // ---- then the paths that arrive from the lane to the left ----
+            // ---- delete paths that arrive from the lane to the left ----
             for (;;) {
-                const float d_left = __shfl_sync(0xffffffffu, d[K - 1], left_lane);
-                float carried = d_left + edge.w; // edge.w = tDD left of this lane's first slot (-inf for lane 0)
+                const float c_out = fmaxf(m[K - 1] + edge.w, d[K - 1] + edge_dd); // D of the right neighbour's first slot
+                float carried = __shfl_sync(0xffffffffu, c_out, left_lane);       // lane 0 receives lane 31's -inf
                 if (!__any_sync(0xffffffffu, carried > d[0])) break;
                 bool crossed = true; // a carried path is still alive after the last column of some lane
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     const int j = 4 * q;
-                    const float4 dd = lds128(dd_lane + q * 512);
+                    const float4 dd = lds128_volatile(dd_lane + q * 512);
                     if (q > 0) {
-                        carried = carried + dd.x;
                         if (!__any_sync(0xffffffffu, carried > d[j])) { // dead everywhere: nothing further can change
                             crossed = false;
                             break;
                         }
                     }
                     d[j] = fmaxf(d[j], carried);
-                    carried = carried + dd.y;
+                    carried = carried + dd.x;
                     d[j + 1] = fmaxf(d[j + 1], carried);
-                    carried = carried + dd.z;
+                    carried = carried + dd.y;
                     d[j + 2] = fmaxf(d[j + 2], carried);
-                    carried = carried + dd.w;
+                    carried = carried + dd.z;
                     d[j + 3] = fmaxf(d[j + 3], carried);
+                    carried = carried + dd.w;
                 }
                 if (!crossed) break;
             }
@@ -225,7 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
                 word = __funnelshift_r(w0, w1, shift);
             }
         }
-        tmem_wait<20>(tq[(Q - 1) & 1]); // retire the group that was requested for a row that does not exist
+        tmem_wait<20>(tq[0]); // retire the group that was requested for a row that does not exist
         if (lane == 0) p.scores[idx] = (CJ_SAME ? J : C) + move;
     }
 
