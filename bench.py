@@ -217,7 +217,52 @@ def other_configs(torch, msv, _cabi, device: int) -> dict:
     leng, model = load("2405.hmm")
     config5 = round(gcups(model, long_resident, len(long_db), leng, long_db.total_residues), 1)
     return {"unit": "GCUPS, device-resident", "config3_model_sweep_100k_sequences": config3,
-            "config5_2405hmm_2048_long_sequences": config5}
+            "config5_2405hmm_2048_long_sequences": config5, "viterbi": viterbi_side_line(torch, msv, _cabi, resident, sweep_db, device)}
+
+
+def viterbi_side_line(torch, msv, _cabi, resident, database, device: int) -> dict:
+    """SURVEY section 8(f) rank 4, the Plan-7 local Viterbi scan (match/insert/delete) on 1400.hmm x the config-3 database:
+    same GCUPS definition as the headline (LENG x residues / time), a sample checked bit-for-bit against
+    oracle/viterbi_oracle.c (the checker; it is never on the measured path) and that oracle's speed on the host cores."""
+    if os.path.join(REPO, "tests") not in sys.path:
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+    from oracle_lib import Oracle, pack
+    oracle = Oracle()
+    h = oracle.load_hmm(os.path.join(REPO, "fixtures", "profile_HMMs", "1400.hmm"))
+    leng = h["model_length"] - 1
+    model = msv.ViterbiModel(_cabi.emission_table(h["match_emissions"]), _cabi.viterbi_transitions(h["transitions"]),
+                             *_cabi.model_transitions(h["model_length"]), device=device)
+    stream = torch.cuda.current_stream()
+    scores = torch.empty(len(database), dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        resident.viterbi_device(model, scores, stream.cuda_stream)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(3):
+        resident.viterbi_device(model, scores, stream.cuda_stream)
+    t1.record(stream)
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / 3
+    rng = np.random.default_rng(4)
+    sample = rng.choice(len(database), size=256, replace=False)
+    off = database.offsets
+    sc, so = pack([database.residues[int(off[q]):int(off[q + 1])] for q in sample])
+    table, tr3 = oracle.prepare(h["match_emissions"])
+    cores = os.cpu_count() or 1
+    t_cpu = time.perf_counter()
+    want = oracle.viterbi_score_batch(table, oracle.viterbi_prepare(h["transitions"]), tr3, sc, so, threads=cores)
+    t_cpu = time.perf_counter() - t_cpu
+    got = scores.cpu().numpy()[sample]
+    gcups = leng * float(database.total_residues) / ms / 1e6
+    # per cell: 7 fp32 adds + 6 two-input maxima (4-way M, 2-way I, 2-way D, E) = 13 lane-ops; the FMNMX pipe (64 lanes/clk/SM,
+    # 3 FMNMX + 1.5 FMNMX3 per cell) allows 14.2 cells/clk/SM, instruction issue (about 13.3 instructions per cell with
+    # the operand loads) 9.6
+    return {"workload": "1400.hmm x 100000 synthetic sequences (config-3 database), device-resident", "gcups": round(gcups, 1),
+            "ms": round(ms, 3), "cells_per_clk_per_sm": round(gcups * 1e9 / 148 / 1.965e9, 2), "geometry": model.geometry,
+            "frac_of_fp32_alu_roofline_13_ops_per_cell": round(gcups * 1e9 * 13 / (148 * 128 * 1.965e9), 3),
+            "mismatches_vs_oracle": int((got.view(np.uint32) != want.view(np.uint32)).sum()), "compared": int(sample.size),
+            "oracle_gcups": round(leng * float(so[-1]) / t_cpu / 1e9, 3), "oracle_threads": cores}
 
 
 # ---- our arm ----------------------------------------------------------------------------------------------------------
