@@ -32,7 +32,7 @@ DECLARED_SYMBOLS = (
     "msv_cuda_db_filter_device", "msv_cuda_db_score_filter", "msv_cuda_host_register", "msv_cuda_host_unregister",
     "msv_cuda_launch_count",
     "msv_host_viterbi_transitions", "msv_cuda_viterbi_model_create", "msv_cuda_viterbi_model_destroy",
-    "msv_cuda_viterbi_model_geometry", "msv_cuda_db_viterbi_device", "msv_cuda_db_viterbi", "msv_cuda_viterbi_batch",
+    "msv_cuda_viterbi_model_geometry", "msv_cuda_db_viterbi_device", "msv_cuda_db_viterbi", "msv_cuda_db_viterbi_filter", "msv_cuda_viterbi_batch",
 )
 
 
@@ -88,6 +88,7 @@ lib.msv_cuda_viterbi_model_destroy.argtypes = [C.c_void_p]
 lib.msv_cuda_viterbi_model_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
 lib.msv_cuda_db_viterbi_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_db_viterbi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+lib.msv_cuda_db_viterbi_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_viterbi_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.msv_cuda_launch_count.restype = C.c_uint64
 lib.msv_cuda_launch_count.argtypes = [C.c_int]
@@ -292,6 +293,13 @@ class Database:
         out = np.empty(self.n, np.float32)
         check(lib.msv_cuda_db_viterbi(model.handle, self.handle, out.ctypes.data))
         return out
+
+    def viterbi_filter(self, model: "ViterbiModel", mu: float, lam: float):
+        """Raw scores, bit scores and Gumbel P-values of the Viterbi scan (host arrays)."""
+        scores, bits, p = (np.empty(self.n, np.float32) for _ in range(3))
+        check(lib.msv_cuda_db_viterbi_filter(model.handle, self.handle, float(mu), float(lam), scores.ctypes.data, bits.ctypes.data,
+                                             p.ctypes.data))
+        return scores, bits, p
 
     def viterbi_device(self, model: "ViterbiModel", scores_device, stream: int = 0) -> None:
         check(lib.msv_cuda_db_viterbi_device(model.handle, self.handle, _ptr(scores_device), stream))

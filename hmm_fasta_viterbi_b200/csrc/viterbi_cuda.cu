@@ -215,6 +215,30 @@ int msv_cuda_db_viterbi(msv_viterbi_model* model, msv_db* db, float* scores_host
     return MSV_OK;
 }
 
+int msv_cuda_db_viterbi_filter(msv_viterbi_model* model, msv_db* db, float mu, float lambda, float* scores_host, float* bits_host,
+                               float* pvalues_host) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (db->n == 0) return MSV_OK;
+    if (!scores_host) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_host is NULL");
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    if (db->cap_stats < db->n) {
+        cudaFree(db->d_stats);
+        db->d_stats = nullptr;
+        db->cap_stats = 0;
+        MSV_CUDA_TRY(cudaMalloc(&db->d_stats, 2 * db->cap_n * sizeof(float)));
+        db->cap_stats = db->cap_n;
+    }
+    float* d_bits = db->d_stats;
+    float* d_p = db->d_stats + db->cap_stats;
+    if (int rc = msv_cuda_db_viterbi_device(model, db, db->d_scores, nullptr)) return rc;
+    if (int rc = msv_cuda_db_filter_device(db, db->d_scores, mu, lambda, d_bits, d_p, nullptr)) return rc;
+    MSV_CUDA_TRY(cudaMemcpy(scores_host, db->d_scores, db->n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (bits_host) MSV_CUDA_TRY(cudaMemcpy(bits_host, d_bits, db->n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (pvalues_host) MSV_CUDA_TRY(cudaMemcpy(pvalues_host, d_p, db->n * sizeof(float), cudaMemcpyDeviceToHost));
+    return MSV_OK;
+}
+
 int msv_cuda_viterbi_batch(msv_viterbi_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host) {
     if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
     if (n && (!offsets || !scores_host)) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");

@@ -74,3 +74,16 @@ std::vector<Log_score> Viterbi_HMM::parallel_run_on_sequences(const Device_datab
     if (status != MSV_OK) throw_viterbi_error("Viterbi_HMM::parallel_run_on_sequences", status);
     return scores;
 }
+
+std::vector<MSV_hit> Viterbi_HMM::viterbi_filter(const Device_database& database, float threshold) {
+    if (database.device() != device_index) set_device(database.device());
+    const auto n = database.size();
+    auto scores = std::vector<float>(n), bits = std::vector<float>(n), p_values = std::vector<float>(n);
+    const auto status =
+        msv_cuda_db_viterbi_filter(on_device(), database.handle(), mu, lambda, scores.data(), bits.data(), p_values.data());
+    if (status != MSV_OK) throw_viterbi_error("Viterbi_HMM::viterbi_filter", status);
+    auto hits = std::vector<MSV_hit>();
+    for (size_t q = 0; q < n; ++q)
+        if (p_values[q] <= threshold) hits.push_back(MSV_hit{q, scores[q], bits[q], p_values[q]});
+    return hits;
+}

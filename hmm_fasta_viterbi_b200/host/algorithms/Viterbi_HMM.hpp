@@ -30,6 +30,10 @@ class Viterbi_HMM {
     // database already resident in HBM (shared with MSV_HMM: upload once, run both scans)
     std::vector<Log_score> parallel_run_on_sequences(const Device_database& database);
 
+    // The Viterbi *filter*, second stage of HMMER3's pipeline: scan, bit scores and Gumbel P-values (STATS LOCAL VITERBI) on
+    // the device; keeps sequences with P <= threshold (HMMER3's default F2 is 1e-3).  Hits reuse MSV_hit.
+    std::vector<MSV_hit> viterbi_filter(const Device_database& database, float threshold = 1e-3f);
+
     size_t length() const { return model_length; } // LENG + 1
     int device() const { return device_index; }
     void set_device(int device);

@@ -204,3 +204,17 @@ Packed_sequences Packed_sequences::slice(size_t first, size_t last) const {
     for (auto q = first; q <= last; ++q) part.offsets[q - first] = offsets[q] - offsets[first];
     return part;
 }
+
+Packed_sequences Packed_sequences::subset(const std::vector<size_t>& indices) const {
+    auto part = Packed_sequences();
+    auto total = uint64_t(0);
+    for (const auto q : indices) total += offsets.at(q + 1) - offsets[q];
+    part.residues.reserve(total);
+    part.offsets.reserve(indices.size() + 1);
+    for (const auto q : indices) {
+        part.residues.insert(part.residues.end(), residues.begin() + static_cast<std::ptrdiff_t>(offsets[q]),
+                             residues.begin() + static_cast<std::ptrdiff_t>(offsets[q + 1]));
+        part.offsets.push_back(part.residues.size());
+    }
+    return part;
+}

@@ -57,4 +57,6 @@ struct Packed_sequences {
     // parts + 1 boundaries of contiguous slices with (nearly) equal residue counts.
     std::vector<size_t> cell_balanced_bounds(int parts) const;
     Packed_sequences slice(size_t first, size_t last) const;
+    // the listed sequences, in the listed order (e.g. the survivors of a filter stage)
+    Packed_sequences subset(const std::vector<size_t>& indices) const;
 };

@@ -173,6 +173,11 @@ int msv_cuda_viterbi_model_geometry(const msv_viterbi_model* model, int* columns
 int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scores_device, void* cuda_stream);
 /* resident database, host result (synchronous). */
 int msv_cuda_db_viterbi(msv_viterbi_model* model, msv_db* db, float* scores_host);
+/* Viterbi scan + filter statistics on a resident database (the second stage of HMMER3's pipeline: bit score against the
+ * null length model and Gumbel P-value with the model's "STATS LOCAL VITERBI" mu / lambda, same formulas as
+ * msv_cuda_db_filter_device); n floats per host array, bits_host / pvalues_host may be NULL. */
+int msv_cuda_db_viterbi_filter(msv_viterbi_model* model, msv_db* db, float mu, float lambda, float* scores_host, float* bits_host,
+                               float* pvalues_host);
 /* HOST buffers in and out: upload + bucket + scan + download in one synchronous call. */
 int msv_cuda_viterbi_batch(msv_viterbi_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host);
 

@@ -72,7 +72,18 @@ int main(int argc, char** argv) {
     CHECK(bounds.size() == 4 && bounds.front() == 0 && bounds.back() == 4);
     const auto part = packed.slice(1, 3);
     CHECK(part.size() == 2 && part.to_sequence(0) == fasta.sequences[1] && part.to_sequence(1) == fasta.sequences[2]);
+    const auto picked = packed.subset({3, 0, 3});
+    CHECK(picked.size() == 3 && picked.to_sequence(0) == fasta.sequences[3] && picked.to_sequence(1) == fasta.sequences[0] &&
+          picked.to_sequence(2) == fasta.sequences[3] && picked.offsets.back() == picked.residues.size());
+    CHECK(packed.subset({}).size() == 0);
     auto threw = false;
+    try {
+        packed.subset({4});
+    } catch (const std::out_of_range&) {
+        threw = true;
+    }
+    CHECK(threw);
+    threw = false;
     try {
         Packed_sequences::from_sequences({"#ACDX"});
     } catch (const std::out_of_range&) {

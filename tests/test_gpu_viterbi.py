@@ -188,3 +188,51 @@ def test_full_size_properties(oracle):
     all_seqs = [database.residues[int(off[q]):int(off[q + 1])] for q in range(2000)]
     pc, po = pack([all_seqs[q] for q in perm])
     assert ubits(model.score_batch(pc, po)).tolist() == ubits(first[:2000][perm]).tolist()
+
+
+def test_viterbi_filter_statistics(oracle):
+    """Bit score against the null length model and Gumbel P-value with STATS LOCAL VITERBI (HMMER3's second filter stage):
+    raw scores bit-exact, statistics within 1e-6 relative of an fp64 host evaluation (they are ordinary floating point)."""
+    import math
+    name = "400.hmm"
+    h = oracle.load_hmm(hmm_path(name))
+    mu, lam = float(h["stats"][2]), float(h["stats"][3])
+    model, table, logtr, tr3 = viterbi_model(oracle, h["match_emissions"], h["transitions"])
+    rng = np.random.default_rng(21)
+    codes, offsets = random_db(rng, 500, 1, 300)
+    db = msv.Database(codes, offsets)
+    scores, bits, p = db.viterbi_filter(model, mu, lam)
+    want = oracle.viterbi_score_batch(table, logtr, tr3, codes, offsets, threads=CORES)
+    assert ubits(scores).tolist() == ubits(want).tolist()
+    for q in range(0, 500, 7):
+        L = int(offsets[q + 1] - offsets[q])
+        null1 = L * math.log(L / (L + 1.0)) + math.log(1.0 / (L + 1.0))
+        b = (float(want[q]) - null1) / math.log(2.0)
+        pv = -math.expm1(-math.exp(-lam * (b - mu)))
+        assert abs(bits[q] - b) <= 1e-6 * max(1.0, abs(b))
+        assert abs(p[q] - pv) <= 1e-5 * max(pv, 1e-30)
+    # the C++ class returns the same hits
+    prof = msv.Profile_HMM(hmm_path(name))
+    assert prof.stats_local_viterbi_mu == np.float32(mu) and prof.stats_local_viterbi_lambda == np.float32(lam)
+
+
+def test_msv_scan_two_stage_pipeline(tmp_path):
+    """tools/msv_scan --viterbi: MSV filter, then the survivors rescored by Viterbi_HMM (first two stages of HMMER3's
+    pipeline).  A sequence sampled from the model's consensus must survive both stages; random sequences must not."""
+    import subprocess
+    from conftest import REPO
+    exe = os.path.join(REPO, "build", "msv_scan")
+    if not os.path.exists(exe):
+        pytest.skip("build/msv_scan not built")
+    prof = msv.Profile_HMM(hmm_path("300.hmm"))
+    consensus = "".join("ACDEFGHIKLMNPQRSTVWY"[int(np.argmax(row))] for row in prof.match_emissions[1:])
+    rng = np.random.default_rng(8)
+    fasta = tmp_path / "db.fsa"
+    with open(fasta, "w") as f:
+        for q in range(200):
+            f.write(f">r{q}\n" + "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWY"), size=int(rng.integers(50, 400)))) + "\n")
+        f.write(">homolog\n" + consensus[40:120] + consensus[150:260] + "\n")  # a deletion of 30 columns inside the hit
+    out = subprocess.run([exe, "--viterbi", hmm_path("300.hmm"), str(fasta)], capture_output=True, text=True, check=True)
+    rows = [line.split("\t") for line in out.stdout.splitlines() if not line.startswith("#")]
+    assert [r[1] for r in rows] == ["200"], out.stdout + out.stderr
+    assert float(rows[0][5]) < 1e-6 and float(rows[0][8]) < 1e-6 and float(rows[0][6]) > 100.0
