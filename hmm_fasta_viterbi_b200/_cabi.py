@@ -28,7 +28,7 @@ DECLARED_SYMBOLS = (
     "msv_host_partition_by_cells",
     "msv_cuda_model_create", "msv_cuda_model_destroy", "msv_cuda_model_geometry", "msv_cuda_model_plan",
     "msv_cuda_db_create", "msv_cuda_db_destroy", "msv_cuda_db_info",
-    "msv_cuda_db_score_device", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
+    "msv_cuda_db_score_device", "msv_cuda_db_score_gather", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
     "msv_cuda_db_filter_device", "msv_cuda_db_score_filter", "msv_cuda_host_register", "msv_cuda_host_unregister",
     "msv_cuda_launch_count",
     "msv_host_viterbi_transitions", "msv_cuda_viterbi_model_create", "msv_cuda_viterbi_model_destroy",
@@ -74,6 +74,7 @@ lib.msv_cuda_db_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, 
 lib.msv_cuda_db_destroy.argtypes = [C.c_void_p]
 lib.msv_cuda_db_info.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 lib.msv_cuda_db_score_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.msv_cuda_db_score_gather.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_size_t, C.c_void_p]
 lib.msv_cuda_db_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.msv_cuda_score_sequence.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, _fp]
@@ -303,6 +304,12 @@ class Database:
 
     def viterbi_device(self, model: "ViterbiModel", scores_device, stream: int = 0) -> None:
         check(lib.msv_cuda_db_viterbi_device(model.handle, self.handle, _ptr(scores_device), stream))
+
+    def score_gather(self, model: Model, gathered, first_index: int, stream: int = 0) -> None:
+        """Scan fused with the gather: scores go to gathered[r][first_index + q] for every array of `gathered` (this GPU's and
+        the peers' copies of the whole score array: device pointers or torch CUDA tensors)."""
+        ptrs = (C.c_void_p * len(gathered))(*[_ptr(g) for g in gathered])
+        check(lib.msv_cuda_db_score_gather(model.handle, self.handle, ptrs, len(gathered), first_index, stream))
 
     def filter_device(self, scores_device, mu: float, lam: float, bits_device=None, pvalues_device=None, stream: int = 0) -> None:
         """Bit scores and Gumbel P-values (HMMER3 MSV filter conventions) from raw scores resident on the device."""

@@ -457,7 +457,7 @@ Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, 
 
 // One launch of the scan over sequences [first, first+count) of `db`; scores go to d_scores[first ..).
 int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64_t residues, int queue_slot, float* d_scores,
-                cudaStream_t stream) {
+                cudaStream_t stream, float* const* mirrors = nullptr, int n_mirrors = 0) {
     if (count == 0) return MSV_OK;
     const Launch_plan chosen = plan_launch(model, db, first, count, residues);
     const msv_model::Plan& plan = *chosen.plan;
@@ -476,6 +476,8 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     p.tr_B_Mk = model->tr_B_Mk;
     p.tr_E_C = model->tr_E_C;
     p.tr_E_J = model->tr_E_J;
+    p.n_mirrors = static_cast<uint32_t>(n_mirrors);
+    for (int r = 0; r < n_mirrors; ++r) p.mirrors[r] = mirrors[r] + first;
     MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue + queue_slot, 0, sizeof(unsigned int), stream));
     // persistent CTAs, at most one per SM; a "slot" scans one sequence at a time (lane group, warp or four warps)
     const size_t threads_per_slot = static_cast<size_t>(geo->G);
@@ -814,6 +816,22 @@ int msv_cuda_db_score_device(msv_model* model, msv_db* db, float* scores_device,
     Device_guard guard(model->device);
     MSV_CUDA_TRY(guard.status);
     return launch_scan(model, db, 0, db->n, db->total, 0, scores_device, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int msv_cuda_db_score_gather(msv_model* model, msv_db* db, float* const* gathered, int n_gathered, size_t first_index,
+                             void* cuda_stream) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (model->device != db->device) return fail(MSV_ERR_INVALID_ARGUMENT, "model and database live on different devices");
+    if (n_gathered < 1 || n_gathered > msv::kMaxScoreMirrors + 1 || !gathered)
+        return fail(MSV_ERR_INVALID_ARGUMENT, "between 1 and %d gathered arrays are supported", msv::kMaxScoreMirrors + 1);
+    for (int r = 0; r < n_gathered; ++r)
+        if (db->n && !gathered[r]) return fail(MSV_ERR_INVALID_ARGUMENT, "gathered[%d] is NULL", r);
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    float* shifted[msv::kMaxScoreMirrors + 1];
+    for (int r = 0; r < n_gathered; ++r) shifted[r] = gathered[r] + first_index;
+    return launch_scan(model, db, 0, db->n, db->total, 0, shifted[0], static_cast<cudaStream_t>(cuda_stream), shifted + 1,
+                       n_gathered - 1);
 }
 
 int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host) {

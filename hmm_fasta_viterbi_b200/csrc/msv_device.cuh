@@ -8,6 +8,7 @@ namespace msv {
 
 constexpr int kAlphabet = 20;
 constexpr int kMaxColumnsPerLane = 88;
+constexpr int kMaxScoreMirrors = 7; // a fused gather reaches the other GPUs of an 8-GPU NVSwitch domain
 constexpr uint32_t kResiduePadBytes = 64; // bytes readable past the last residue of the database
 
 struct Scan_params {
@@ -22,7 +23,17 @@ struct Scan_params {
     uint32_t n;
     uint32_t table_bytes;
     float tr_B_Mk, tr_E_C, tr_E_J;
+    // fused gather: every score is also stored into these buffers (peer GPUs' copies of the gathered score array, mapped
+    // into this GPU's address space over NVLink; already offset to this shard's first sequence).  0 = plain scan.
+    uint32_t n_mirrors;
+    float* mirrors[kMaxScoreMirrors];
 };
+
+// the one store per sequence: local result plus, for the fused gather, the same 4 bytes into every peer's array
+__device__ __forceinline__ void store_score(const Scan_params& p, uint32_t idx, float score) {
+    p.scores[idx] = score;
+    for (uint32_t r = 0; r < p.n_mirrors; ++r) p.mirrors[r][idx] = score;
+}
 
 // ---- mbarrier / bulk-async (TMA) helpers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
         // ---- retire finished sequences, pull new ones (group-uniform control flow) ----
         while (remaining == 0 && !done) {
             if (active) {
-                if (gl == 0) p.scores[idx] = (CJ_SAME ? J : C) + move; // MSV_HMM.cpp:112
+                if (gl == 0) store_score(p, idx, (CJ_SAME ? J : C) + move); // MSV_HMM.cpp:112
                 active = false;
             }
             uint32_t ticket = 0;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
             row(word & 0xffu, (word >> 8) & 0xffu);
             word >>= 8;
         }
-        if (lane == 0) p.scores[idx] = (CJ_SAME ? J : C) + move; // MSV_HMM.cpp:112
+        if (lane == 0) store_score(p, idx, (CJ_SAME ? J : C) + move); // MSV_HMM.cpp:112
     }
 
     if constexpr (KT > 0) {
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_quad_kernel(const Scan_pa
             row(word & 0xffu);
             word >>= 8;
         }
-        if (wq == 0 && lane == 0) p.scores[idx] = (CJ_SAME ? J : C) + move;
+        if (wq == 0 && lane == 0) store_score(p, idx, (CJ_SAME ? J : C) + move);
     }
 
     if constexpr (KT > 0) {

@@ -193,6 +193,7 @@ int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scor
     p.tr_B_Mk = model->tr_B_Mk;
     p.tr_E_C = model->tr_E_C;
     p.tr_E_J = model->tr_E_J;
+    p.n_mirrors = 0;
     MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, sizeof(unsigned int), stream));
     // persistent CTAs, one per SM, one warp per sequence in flight; fewer warps when there are fewer sequences
     const size_t warps_per_cta = static_cast<size_t>(geo->threads) / 32;

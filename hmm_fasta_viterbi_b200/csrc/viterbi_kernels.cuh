@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
             }
         }
         tmem_wait<20>(tq[0]); // retire the group that was requested for a row that does not exist
-        if (lane == 0) p.scores[idx] = (CJ_SAME ? J : C) + move;
+        if (lane == 0) store_score(p, idx, (CJ_SAME ? J : C) + move);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -109,6 +109,15 @@ int msv_cuda_db_info(const msv_db* db, size_t* n, uint64_t* total_residues, uint
 /* resident path: scores_device is a DEVICE pointer to n floats (original sequence order); asynchronous on
  * `cuda_stream` (a cudaStream_t passed as void*, NULL = default stream). */
 int msv_cuda_db_score_device(msv_model* model, msv_db* db, float* scores_device, void* cuda_stream);
+/* Scan fused with the gather of a sharded run (one process per GPU, NVLink / NVSwitch): `gathered[r]`, r < n_gathered <= 8,
+ * are DEVICE-ADDRESSABLE pointers to every participant's copy of the whole gathered score array -- this GPU's own copy
+ * and the peers' copies mapped into this process (CUDA IPC / symmetric memory; torch.distributed._symmetric_memory in
+ * bench.py).  The kernel stores the score of local sequence q into gathered[r][first_index + q] for every r, straight
+ * from the lane that computed it, so no collective follows the scan: after a barrier every GPU holds all scores.
+ * (The reference has no multi-device path; the NCCL all-gather of msv_cuda_db_score_device's output is the plain
+ * alternative.)  Asynchronous on `cuda_stream`. */
+int msv_cuda_db_score_gather(msv_model* model, msv_db* db, float* const* gathered, int n_gathered, size_t first_index,
+                             void* cuda_stream);
 /* resident database, host result: synchronous, copies n floats into scores_host. */
 int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host);
 /* end-to-end path with HOST buffers in and out: upload + bucket + scan + download in one synchronous call.

@@ -518,3 +518,42 @@ def test_reference_programs_run_unchanged(prog, cwd):
     run = subprocess.run([exe], cwd=os.path.join(REPO, "build", cwd), capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "failed" not in run.stdout
+
+
+# ---- scan fused with the gather (msv_cuda_db_score_gather) ---------------------------------------------------------------
+def test_score_gather_writes_every_copy(oracle):
+    """One GPU standing in for several: three 'copies' of the gathered array on the same device.  Every copy must hold
+    this shard's scores at first_index.. and stay untouched elsewhere."""
+    import torch
+    model, table, tr3 = device_model(oracle, "1400.hmm")
+    rng = np.random.default_rng(77)
+    seqs, codes, offsets = random_db(rng, 3000, 0, 300)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    db = msv.Database(codes, offsets)
+    first, total = 1234, 6000
+    copies = [torch.full((total,), float("nan"), dtype=torch.float32, device="cuda") for _ in range(3)]
+    db.score_gather(model, copies, first)
+    torch.cuda.synchronize()
+    for c in copies:
+        got = c.cpu().numpy()
+        assert ubits(got[first:first + 3000]).tolist() == ubits(want).tolist()
+        assert np.isnan(got[:first]).all() and np.isnan(got[first + 3000:]).all()
+    with pytest.raises(msv.MsvCudaError):
+        db.score_gather(model, copies * 3, 0)  # more than 8 copies
+
+
+def test_fused_gather_two_gpus(tmp_path):
+    """torchrun x 2: each rank scans its shard and stores straight into both ranks' symmetric buffers; the result must
+    equal the NCCL all-gather of the plain scan on every rank (bench.py's peer_gather leg)."""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = subprocess.run(
+        ["python", "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+         "--master-port", "29731", os.path.join(REPO, "bench.py"), "--gpus", "2", "--steps", "2", "--warmup", "3", "--sequences", "50000"],
+        capture_output=True, text=True, cwd=REPO, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and "peer_gather" in line
+    assert line["peer_gather"].get("equals_nccl_all_gather_on_every_rank") is True, line["peer_gather"]
