@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--model", default=MODEL_FILE)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the bounded baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-peer-gather", action="store_true", help="N > 1: skip the fused scan+gather (peer memory) measurement")
+    ap.add_argument("--no-peer-gather", action="store_true", help="N > 1: gather the scores with NCCL instead of the fused peer-memory stores")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short config-3 / config-5 side measurements")
     return ap.parse_args()
 
@@ -319,7 +319,7 @@ def main() -> None:
     gathered = torch.empty((world * max(n_max, 1),), dtype=torch.float32, device="cuda") if world > 1 else None
     stream = torch.cuda.current_stream()
 
-    def step() -> None:
+    def nccl_step() -> None:
         db.score_device(model, scores, stream.cuda_stream)
         if world > 1:
             dist.all_gather_into_tensor(gathered, scores)
@@ -329,6 +329,35 @@ def main() -> None:
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # N > 1: the product path FUSES the gather into the scan -- every rank's kernel stores its scores straight into all ranks'
+    # copies of the gathered array over NVLink peer memory (torch symmetric memory provides the mapped pointers), followed
+    # by one device-side barrier; no collective.  The plain scan + NCCL all-gather is measured next to it (`nccl_gather`).
+    step, gather_kind, peer_error, symmetric = nccl_step, "nccl all_gather_into_tensor", None, None
+    if world > 1 and not args.no_peer_gather:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            slot = max(n_max, 1)
+            symmetric = symm_mem.empty(world * slot, dtype=torch.float32, device=torch.device("cuda", local))
+            symmetric.fill_(float("nan"))
+            handle = symm_mem.rendezvous(symmetric, dist.group.WORLD)
+            copies = [int(handle.buffer_ptrs[rank])] + [int(handle.buffer_ptrs[r]) for r in range(world) if r != rank]
+
+            def peer_step() -> None:
+                db.score_gather(model, copies, rank * slot, stream.cuda_stream)
+                handle.barrier(channel=0)
+
+            peer_step()
+            fence()
+            ok = torch.tensor([1.0], device="cuda")
+        except Exception as e:  # noqa: BLE001 -- needs P2P over NVLink; fall back to the NCCL gather and say so
+            peer_error = f"{type(e).__name__}: {e}"[:300]
+            ok = torch.tensor([0.0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank must take the same path
+        if float(ok.item()) == 1.0:
+            step, gather_kind = peer_step, "fused into the scan kernel: stores to every rank's copy over NVLink peer memory"
+        else:
+            symmetric = None
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -348,6 +377,23 @@ def main() -> None:
     clocks = sampler.stop()
     ms_total = start.elapsed_time(stop)
 
+    # ---- comparison: plain scan + NCCL all-gather, and the two gathered arrays must be the same bits ----
+    nccl_gather = None
+    if world > 1 and symmetric is not None:
+        for _ in range(3):
+            nccl_step()
+        fence()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record(stream)
+        for _ in range(args.steps):
+            nccl_step()
+        n1.record(stream)
+        fence()
+        same = bool(torch.equal(symmetric.view(torch.int32), gathered.view(torch.int32)))
+        flags = torch.tensor([n0.elapsed_time(n1), 0.0 if same else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        nccl_gather = {"ms_total": float(flags[0].item()), "same_bits_as_fused_gather_on_every_rank": float(flags[1].item()) == 0.0}
+
     # ---- the scan kernel alone (for the roofline), same launches, no gather ----
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record(stream)
@@ -356,39 +402,6 @@ def main() -> None:
     k1.record(stream)
     fence()
     kernel_ms = k0.elapsed_time(k1) / args.steps
-
-    # ---- the same step with the gather FUSED into the scan: every rank's kernel stores its scores straight into all ranks'
-    # copies of the gathered array over NVLink (symmetric memory), then one device-side barrier; no collective ----
-    peer_gather = None
-    if world > 1 and not args.no_peer_gather:
-        try:
-            import torch.distributed._symmetric_memory as symm_mem
-            slot = max(n_max, 1)
-            symmetric = symm_mem.empty(world * slot, dtype=torch.float32, device=torch.device("cuda", local))
-            symmetric.fill_(float("nan"))
-            handle = symm_mem.rendezvous(symmetric, dist.group.WORLD)
-            copies = [int(handle.buffer_ptrs[rank])] + [int(handle.buffer_ptrs[r]) for r in range(world) if r != rank]
-
-            def peer_step() -> None:
-                db.score_gather(model, copies, rank * slot, stream.cuda_stream)
-                handle.barrier(channel=0)
-
-            fence()
-            for _ in range(3):
-                peer_step()
-            fence()
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record(stream)
-            for _ in range(args.steps):
-                peer_step()
-            p1.record(stream)
-            fence()
-            same = bool(torch.equal(symmetric.view(torch.int32), gathered.view(torch.int32)))
-            flags = torch.tensor([p0.elapsed_time(p1), 0.0 if same else 1.0], dtype=torch.float64, device="cuda")
-            dist.all_reduce(flags, op=dist.ReduceOp.MAX)
-            peer_gather = {"ms_total": float(flags[0].item()), "equals_nccl_all_gather_on_every_rank": float(flags[1].item()) == 0.0}
-        except Exception as e:  # noqa: BLE001 -- symmetric memory needs P2P over NVLink; report instead of failing the bench
-            peer_gather = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     # ---- e2e: host buffers through msv_cuda_score_batch (H2D + bucketing + scan + D2H) ----
     for _ in range(2):
@@ -462,13 +475,14 @@ def main() -> None:
             "roofline": roofline,
             "parity": parity,
         }
-        if peer_gather is not None:
-            if "ms_total" in peer_gather:
-                ms_peer = peer_gather.pop("ms_total")
-                peer_gather = {"value": cells_job * args.steps / (ms_peer / 1e3) / 1e9, "unit": "GCUPS", "ms_per_step": ms_peer / args.steps,
-                               "what": "scan kernels store their scores into every rank's gathered array over NVLink peer memory "
-                                       "(msv_cuda_db_score_gather + symmetric-memory barrier) instead of scan + NCCL all-gather"} | peer_gather
-            out["peer_gather"] = peer_gather
+        if world > 1:
+            out["config"]["gather"] = gather_kind
+            if nccl_gather is not None:
+                ms_nccl = nccl_gather.pop("ms_total")
+                out["nccl_gather"] = {"value": cells_job * args.steps / (ms_nccl / 1e3) / 1e9, "unit": "GCUPS",
+                                      "ms_per_step": ms_nccl / args.steps, "what": "plain scan + NCCL all_gather_into_tensor"} | nccl_gather
+            if peer_error is not None:
+                out["peer_gather_unavailable"] = peer_error
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             kind, scorer = cpu_reference_scorer(model_path)
