@@ -331,21 +331,16 @@ def main() -> None:
             torch.cuda.synchronize()
 
     # N > 1: the product path FUSES the gather into the scan -- every rank's kernel stores its scores straight into all ranks'
-    # copies of the gathered array over NVLink peer memory (torch symmetric memory provides the mapped pointers), followed
-    # by one device-side barrier; no collective.  The plain scan + NCCL all-gather is measured next to it (`nccl_gather`).
+    # copies of the gathered array over NVLink peer memory (hmm_fasta_viterbi_b200.sharded.FusedGather), followed by one
+    # device-side barrier; no collective.  The plain scan + NCCL all-gather is measured next to it (`nccl_gather`).
     step, gather_kind, peer_error, symmetric = nccl_step, "nccl all_gather_into_tensor", None, None
     if world > 1 and not args.no_peer_gather:
         try:
-            import torch.distributed._symmetric_memory as symm_mem
-            slot = max(n_max, 1)
-            symmetric = symm_mem.empty(world * slot, dtype=torch.float32, device=torch.device("cuda", local))
-            symmetric.fill_(float("nan"))
-            handle = symm_mem.rendezvous(symmetric, dist.group.WORLD)
-            copies = [int(handle.buffer_ptrs[rank])] + [int(handle.buffer_ptrs[r]) for r in range(world) if r != rank]
+            fused = sharded.FusedGather(n_max, torch.device("cuda", local))
+            symmetric = fused.scores
 
             def peer_step() -> None:
-                db.score_gather(model, copies, rank * slot, stream.cuda_stream)
-                handle.barrier(channel=0)
+                fused.scan(model, db, stream.cuda_stream)
 
             peer_step()
             fence()

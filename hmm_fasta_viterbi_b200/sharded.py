@@ -1,7 +1,9 @@
 """Sharding a sequence database over ranks (one process per GPU) and gathering the per-sequence scores.
 
-The scan has no exchange step: sequences are independent and the model is replicated.  The only collective is the
-gather of fp32 scores at the end (NCCL over NVLink on GPUs; the same code runs over gloo on CPU in the tests).
+The scan has no exchange step: sequences are independent and the model is replicated.  The only exchange is the gather
+of fp32 scores at the end.  On GPUs it is FUSED into the scan (``FusedGather``: the kernel stores every score into all
+ranks' copies of the gathered array over NVLink peer memory, no collective); ``gather_scores`` is the plain
+all-gather (NCCL on GPUs; the same code runs over gloo on CPU in the tests).
 Slices are contiguous and balanced by residue count (= DP cell count for a fixed model), computed by the C ABI helper
 ``msv_host_partition_by_cells``.
 """
@@ -42,3 +44,38 @@ def gather_scores(local_scores, counts, group=None):
     gathered = torch.empty(world * width, dtype=torch.float32, device=local_scores.device)
     dist.all_gather_into_tensor(gathered, padded, group=group)
     return torch.cat([gathered[r * width: r * width + counts[r]] for r in range(world)])
+
+
+class FusedGather:
+    """Scan + gather in one kernel launch per rank (``msv_cuda_db_score_gather``).
+
+    Every rank owns a *symmetric* buffer of ``world * slot`` floats (``torch.distributed._symmetric_memory``); the peers'
+    buffers are mapped into this process over NVLink / NVSwitch.  ``scan(model, database)`` launches the MSV scan of this
+    rank's shard with all ``world`` buffers as destinations -- the lane that finishes sequence q stores its score at
+    ``rank * slot + q`` of every copy -- and then a device-side barrier on the current stream.  When that stream reaches
+    the end of ``scan``, ``self.scores`` holds the whole job's scores on every rank (rank r's shard at
+    ``[r * slot, r * slot + counts[r])``).  Needs one GPU per rank in one NVLink domain; raises whatever symmetric memory
+    raises otherwise -- callers fall back to ``gather_scores``.
+    """
+
+    def __init__(self, slot: int, device, group=None) -> None:
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.slot = dist.get_world_size(group), dist.get_rank(group), max(int(slot), 1)
+        if self.world > 8:
+            raise ValueError("the fused gather addresses at most 8 GPUs (one NVSwitch domain)")
+        self.scores = symm_mem.empty(self.world * self.slot, dtype=torch.float32, device=device)
+        self.scores.fill_(float("nan"))
+        self._handle = symm_mem.rendezvous(self.scores, group)
+        ptrs = [int(p) for p in self._handle.buffer_ptrs]
+        self._copies = [ptrs[self.rank]] + [ptrs[r] for r in range(self.world) if r != self.rank]  # own copy first
+
+    def scan(self, model, database, stream: int = 0) -> None:
+        database.score_gather(model, self._copies, self.rank * self.slot, stream)
+        self._handle.barrier(channel=0)
+
+    def shard(self, r: int, count: int):
+        return self.scores[r * self.slot: r * self.slot + count]
