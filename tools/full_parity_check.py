@@ -15,11 +15,29 @@ import hmm_fasta_viterbi_b200 as msv  # noqa: E402
 from hmm_fasta_viterbi_b200 import _cabi  # noqa: E402
 from oracle_lib import Oracle, RefLib  # noqa: E402
 
-# usage: full_parity_check.py [sequences] [model.hmm] [long]      ("long": config-5 style sequences of 10-35 k residues)
+# usage: full_parity_check.py [sequences] [model.hmm] [long|viterbi]
+#   "long": config-5 style sequences of 10-35 k residues;  "viterbi": the Plan-7 local Viterbi scan against oracle/viterbi_oracle.c
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 model_name = sys.argv[2] if len(sys.argv) > 2 else "1400.hmm"
 long_sequences = len(sys.argv) > 3 and sys.argv[3] == "long"
 model_path = os.path.join(REPO, "fixtures", "profile_HMMs", model_name)
+if len(sys.argv) > 3 and sys.argv[3] == "viterbi":
+    oracle = Oracle()
+    h = oracle.load_hmm(model_path)
+    vit = msv.ViterbiModel(_cabi.emission_table(h["match_emissions"]), _cabi.viterbi_transitions(h["transitions"]),
+                           *_cabi.model_transitions(h["model_length"]))
+    db = msv.Packed_sequences.synthetic_swissprot_like(n, 20261018)
+    gpu = vit.score_batch(db.residues, db.offsets)
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    table, tr3 = oracle.prepare(h["match_emissions"])
+    cpu = oracle.viterbi_score_batch(table, oracle.viterbi_prepare(h["transitions"]), tr3, db.residues, db.offsets, threads)
+    seconds = time.perf_counter() - t0
+    mismatches = int((gpu.view(np.uint32) != cpu.view(np.uint32)).sum())
+    print(json.dumps({"scan": "viterbi", "sequences": n, "residues": int(db.total_residues), "model": model_name,
+                      "checker": "oracle/viterbi_oracle.c (parity unpinned: no reference implementation exists)", "cpu_threads": threads,
+                      "cpu_seconds": round(seconds, 1), "mismatches": mismatches, "geometry": vit.geometry}))
+    sys.exit(1 if mismatches else 0)
 prof = msv.Profile_HMM(model_path)
 model = msv.Model(_cabi.emission_table(prof.match_emissions), *_cabi.model_transitions(prof.model_length))
 db = (msv.Packed_sequences.synthetic_long_uniform(n, 2405, 10_000, 35_000) if long_sequences
