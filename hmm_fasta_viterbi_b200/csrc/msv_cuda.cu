@@ -51,6 +51,7 @@ struct Geometry {
     Scan_kernel fn;         // general transitions
     Scan_kernel fn_cj_same; // tr_E_C == tr_E_J bitwise (C is J); same as fn for the generic family
     int variant = 0;        // 0: tensor-memory columns are each lane's lowest; 1: TMEM_AHEAD (they are the highest, loaded a row ahead)
+    Scan_kernel fn_cj_same_exact = nullptr; // warp family: when fn_cj_same speculates B = N + move (and verifies), the kernel that never does
     size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET) * (K - std::max(KT, 0)) * G * sizeof(float); }
 };
 
@@ -58,9 +59,22 @@ template <int G, int K> constexpr Geometry generic_entry() {
     return Geometry{G, K, -1, threads_for(K), msv::msv_scan_kernel<G, K, threads_for(K), false>,
                     msv::msv_scan_kernel<G, K, threads_for(K), true>};
 }
+// Speculative rows (B = N + move, verified per sequence; msv_kernels.cuh) are instantiated where B200 sweeps showed them
+// ahead of the exact rows (profiles/r01/sweep_speculation*.txt: +13 % at K = 4, +2..6 % at K = 16..22 and 32..38, level at
+// K = 8..14 and 42, 44; behind by 1 % at K = 26..30 and by 5..8 % from K = 48 up, where the two row bodies no longer share
+// the instruction cache).
+constexpr bool speculation_pays(int K) { return K <= 44 && !(K >= 26 && K <= 30); }
+template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_kernel() {
+    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD, true>;
+    else return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD>;
+}
+template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_exact_kernel() {
+    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD>;
+    else return nullptr;
+}
 template <int K, int KT> constexpr Geometry warp_entry() {
     return Geometry{32, K, KT, warp_threads_for(K, KT), msv::msv_scan_warp_kernel<K, KT, warp_threads_for(K, KT), false>,
-                    msv::msv_scan_warp_kernel<K, KT, warp_threads_for(K, KT), true>};
+                    cj_same_kernel<K, KT, warp_threads_for(K, KT), false>(), 0, cj_same_exact_kernel<K, KT, warp_threads_for(K, KT), false>()};
 }
 
 constexpr int quad_threads_for(int K) { return K <= 12 ? 1024 : K <= 28 ? 768 : 512; }
@@ -69,11 +83,13 @@ template <int K, int KT> constexpr Geometry quad_entry() { // four warps (128 la
                     msv::msv_scan_quad_kernel<K, KT, quad_threads_for(K), true>};
 }
 template <int K, int KT, int T> constexpr Geometry warp_entry_threads() {
-    return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false>, msv::msv_scan_warp_kernel<K, KT, T, true>};
+    return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false>, cj_same_kernel<K, KT, T, false>(), 0,
+                    cj_same_exact_kernel<K, KT, T, false>()};
 }
 
 template <int K, int KT, int T> constexpr Geometry warp_entry_ahead() {
-    return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false, true>, msv::msv_scan_warp_kernel<K, KT, T, true, true>, 1};
+    return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false, true>, cj_same_kernel<K, KT, T, true>(), 1,
+                    cj_same_exact_kernel<K, KT, T, true>()};
 }
 
 #define MSV_FOR_EACH_K(X, A)                                                                                           \
@@ -370,6 +386,15 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
     return db_read_validation(db, residues, stream);
 }
 
+} // namespace
+
+namespace msv_detail {
+int db_refill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n) { return db_fill(db, residues, offsets, n, nullptr); }
+int db_free(msv_db* db) { return db_release(db); }
+} // namespace msv_detail
+
+namespace {
+
 // ---- launch planning ------------------------------------------------------------------------------------------------
 // With millions of sequences every plan is balanced and the choice is static.  With few (long) sequences the scan is a
 // scheduling problem: sequences are serial, a slot (warp / four warps) scans one at a time, so the makespan is set by
@@ -488,7 +513,11 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     if (ctas == 1) slots = std::min(slots, count); // do not launch slots that would find the queue empty
     const int threads = static_cast<int>(std::max<size_t>(32, (slots * threads_per_slot + 31) / 32 * 32));
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
-    (cj_same ? geo->fn_cj_same : geo->fn)<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
+    Scan_kernel kernel = cj_same ? geo->fn_cj_same : geo->fn;
+    // databases of long sequences (config 5: 10-35 k residues each) would mostly be scanned twice by the speculative rows
+    const bool long_sequences = residues / count > msv::kSpeculationMaxLength / 2;
+    if (cj_same && geo->fn_cj_same_exact && (long_sequences || std::getenv("MSV_CUDA_NO_SPECULATION"))) kernel = geo->fn_cj_same_exact;
+    kernel<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
     ++g_launches;
     MSV_CUDA_TRY(cudaGetLastError());
     return MSV_OK;
@@ -715,8 +744,8 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < plan.shared_bytes + 1024) return cudaErrorInvalidConfiguration;
         cudaError_t err = cudaMalloc(&plan.d_table, plan.table_bytes);
         if (err == cudaSuccess) err = cudaMemcpy(plan.d_table, laid.data(), plan.table_bytes, cudaMemcpyHostToDevice);
-        for (Scan_kernel fn : {geo->fn, geo->fn_cj_same})
-            if (err == cudaSuccess)
+        for (Scan_kernel fn : {geo->fn, geo->fn_cj_same, geo->fn_cj_same_exact})
+            if (err == cudaSuccess && fn)
                 err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(plan.shared_bytes));
         if (err == cudaSuccess) plan.geo = geo;

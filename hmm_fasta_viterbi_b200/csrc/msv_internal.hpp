@@ -65,3 +65,10 @@ struct msv_db {
     cudaEvent_t stage_copied[kMaxChunks] = {};
     cudaEvent_t reserved = nullptr;
 };
+
+namespace msv_detail {
+// (re)fill a database handle from host buffers on the default stream: upload, validate, bucket longest-first; buffers only
+// grow, so a workspace handle can be refilled call after call without reallocating (msv_cuda.cu)
+int db_refill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n);
+int db_free(msv_db* db);
+} // namespace msv_detail

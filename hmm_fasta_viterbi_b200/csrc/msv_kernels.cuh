@@ -28,6 +28,8 @@
 // bit-identical to the reference for any order of the E reduction.
 #pragma once
 
+#include <type_traits>
+
 #include "msv_device.cuh"
 
 namespace msv {
@@ -190,8 +192,19 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
 //   * TMEM_AHEAD: the tensor-memory columns are the TOP KT columns of each lane and their emissions for row i+1 are
 //     requested while row i is still being computed, so every row starts on operands that are already in registers
 //     (instead of waiting for the first LDS) and the shared-memory loads of the row land behind that work.
-template <int K, int KT, int THREADS, bool CJ_SAME, bool TMEM_AHEAD = false>
+//   * SPECULATE (with CJ_SAME): B[i] = max(N[i], J[i]) + move equals N[i] + move for as long as J <= N, which is the
+//     whole sequence unless it contains a hit worth more than the ~19 nats of entry cost (HMMER 3.1's SSV observation;
+//     ~0.2 % of random sequences).  The speculative row therefore takes B = N + move, which needs no E: the warp-wide
+//     reduction, the uniform->vector move and the J/B maxima leave the row-to-row critical path.  Each lane carries
+//     j = max(j + loop, E_lane + tEJ); rounding is monotone, so max over lanes of j is exactly J as long as the
+//     speculation held.  Verification is one vote per SEQUENCE: if J[i] > N[i] at some row then j >= N from that row on
+//     in the lane that saw it (j and N decay by the same + loop), so "some lane ends with j >= N" catches every
+//     sequence whose B ever differed; those are scanned again with the exact row.  Same bits, always.
+constexpr uint32_t kSpeculationMaxLength = 4096;
+
+template <int K, int KT, int THREADS, bool CJ_SAME, bool TMEM_AHEAD = false, bool SPECULATE = false>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_params p) {
+    constexpr bool SPEC = SPECULATE && CJ_SAME;
     static_assert(KT >= 0 && KT <= 24 && KT % 2 == 0, "TMEM columns per lane");
     constexpr int KS = K - KT;
     static_assert(K % 2 == 0 && KS >= 0 && KS % 4 == 0 && K <= kMaxColumnsPerLane, "columns per lane");
@@ -277,7 +290,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         float J = NEG_INF, C = NEG_INF, N = 0.0f, B = move; // MSV_HMM.cpp:96-97
 
         float te[KT > 0 ? KT : 1]; // emissions of the tensor-memory columns for the row at hand
-        auto row = [&](const uint32_t x, const uint32_t x_next) {
+        auto any_row = [&](auto exact_tag, const uint32_t x, const uint32_t x_next) {
+            constexpr bool EXACT = decltype(exact_tag)::value;
             constexpr bool AHEAD = TMEM_AHEAD && KT > 0;
             if constexpr (KT > 0 && !AHEAD) tmem_load<KT>(tmem_lane_base + x * KT, te);
             const uint32_t erow = tab_lane + x * ROW_BYTES;
@@ -320,13 +334,22 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
                 shared_columns();
                 tensor_columns();
             }
-            float E;
-            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(E) : "f"(e));
-            J = fmaxf(J + loop, E + tEJ);                           // MSV_HMM.cpp:107
-            if constexpr (!CJ_SAME) C = fmaxf(C + loop, E + tEC);   // MSV_HMM.cpp:108
-            N = N + loop;                                           // MSV_HMM.cpp:109
-            B = fmaxf(N, J) + move; // MSV_HMM.cpp:110: max(N+move, J+move) == max(N, J)+move exactly (rounding is monotone)
+            if constexpr (EXACT) {
+                float E;
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(E) : "f"(e));
+                J = fmaxf(J + loop, E + tEJ);                           // MSV_HMM.cpp:107
+                if constexpr (!CJ_SAME) C = fmaxf(C + loop, E + tEC);   // MSV_HMM.cpp:108
+                N = N + loop;                                           // MSV_HMM.cpp:109
+                B = fmaxf(N, J) + move; // MSV_HMM.cpp:110: max(N+move, J+move) == max(N, J)+move exactly (rounding is monotone)
+            } else {
+                J = fmaxf(J + loop, e + tEJ); // this lane's share of J; the lanes are combined once, after the last row
+                N = N + loop;
+                B = N + move;                 // = max(N, J) + move while J <= N -- verified below
+            }
         };
+        using Exact_row = std::bool_constant<true>;
+        using Main_row = std::bool_constant<!SPEC>;
+        auto row = [&](const uint32_t x, const uint32_t x_next) { any_row(Main_row{}, x, x_next); };
 
         // residues arrive as aligned 32-bit words (4 per load, prefetched two words ahead); a funnel shift undoes the
         // byte misalignment of the sequence start.  `word` holds the next four residues, `ahead` the four after them.
@@ -336,7 +359,9 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         wp += 3;
         uint32_t word = __funnelshift_r(w0, w1, shift);
         if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + (word & 0xffu) * KT, te);
-        const uint32_t quads = len >> 2;
+        // long sequences are likely enough to contain a hit that speculating on them would mostly mean scanning them twice
+        const bool speculate = SPEC && len <= kSpeculationMaxLength;
+        const uint32_t quads = (!SPEC || speculate) ? len >> 2 : 0u;
         // 4 rows (one residue word) per loop iteration, 8 or 16 where B200 sweeps showed a gain (+1..4 %, +10 % at K = 4;
         // profiles/r01/sweep_models_v6_row_unroll.jsonl, sweep_force_unroll2.txt).  It is not monotone in K -- the
         // instruction scheduler's luck -- and the longest bodies stop fitting the instruction cache (-10 % at K = 76).
@@ -358,9 +383,29 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
             word = ahead;
         }
 #pragma unroll 1
-        for (uint32_t r = len & 3u; r > 0; --r) {
+        for (uint32_t r = (!SPEC || speculate) ? len & 3u : 0u; r > 0; --r) {
             row(word & 0xffu, (word >> 8) & 0xffu);
             word >>= 8;
+        }
+        if constexpr (SPEC) {
+            if (!speculate || __any_sync(0xffffffffu, J >= N)) {
+                // J may have overtaken N at some row, where B was then not N + move: scan this sequence again, exactly
+                if constexpr (TMEM_AHEAD && KT > 0) tmem_wait<KT>(te); // retire the request made by the last speculative row
+#pragma unroll
+                for (int j = 0; j < K; ++j) m[j] = NEG_INF;
+                J = NEG_INF, N = 0.0f, B = move;
+                const uint8_t* rp = p.residues + begin;
+                uint32_t x = __ldg(rp);
+                if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + x * KT, te);
+#pragma unroll 1
+                for (uint32_t i = 0; i < len; ++i) {
+                    const uint32_t x_next = __ldg(rp + i + 1); // the byte after the last residue is another sequence's or padding
+                    any_row(Exact_row{}, x, x_next);
+                    x = x_next;
+                }
+            } else {
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(J) : "f"(J));
+            }
         }
         if (lane == 0) store_score(p, idx, (CJ_SAME ? J : C) + move); // MSV_HMM.cpp:112
     }

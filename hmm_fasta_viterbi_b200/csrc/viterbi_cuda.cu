@@ -50,6 +50,7 @@ struct msv_viterbi_model {
     float4* d_table = nullptr;
     float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
     int sm_count = 0;
+    msv_db* workspace = nullptr; // reused by msv_cuda_viterbi_batch (grow-only buffers)
 };
 
 extern "C" {
@@ -154,6 +155,7 @@ int msv_cuda_viterbi_model_create(const float* emission_scores, const float* log
 
 int msv_cuda_viterbi_model_destroy(msv_viterbi_model* model) {
     if (!model) return MSV_OK;
+    msv_detail::db_free(model->workspace);
     {
         Device_guard guard(model->device);
         cudaFree(model->d_table);
@@ -243,11 +245,15 @@ int msv_cuda_db_viterbi_filter(msv_viterbi_model* model, msv_db* db, float mu, f
 int msv_cuda_viterbi_batch(msv_viterbi_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host) {
     if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
     if (n && (!offsets || !scores_host)) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
-    msv_db* db = nullptr;
-    if (int rc = msv_cuda_db_create(model->device, residues, offsets, n, &db)) return rc;
-    const int rc = msv_cuda_db_viterbi(model, db, scores_host);
-    msv_cuda_db_destroy(db);
-    return rc;
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    if (!model->workspace) {
+        model->workspace = new (std::nothrow) msv_db();
+        if (!model->workspace) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+        model->workspace->device = model->device;
+    }
+    if (int rc = msv_detail::db_refill(model->workspace, residues, offsets, n)) return rc;
+    return msv_cuda_db_viterbi(model, model->workspace, scores_host);
 }
 
 } // extern "C"

@@ -79,6 +79,8 @@ lib.msvh_viterbi_free.argtypes = [_vp]
 lib.msvh_viterbi_parallel_run_on_sequence.argtypes = [_vp, C.c_char_p, C.POINTER(C.c_float)]
 lib.msvh_viterbi_parallel_run_on_packed.argtypes = [_vp, _vp, _f32]
 lib.msvh_viterbi_parallel_run_on_device_database.argtypes = [_vp, _vp, _f32]
+lib.msvh_viterbi_filter.restype = C.c_long
+lib.msvh_viterbi_filter.argtypes = [_vp, _vp, C.c_float, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msvh_msv_filter.restype = C.c_long
 lib.msvh_msv_filter.argtypes = [_vp, _vp, C.c_float, C.c_size_t, _vp, _vp, _vp, _vp]
 lib.msvh_msv_parallel_run_on_packed_devices.argtypes = [_vp, _vp, C.POINTER(C.c_int), C.c_int, _f32]
@@ -294,6 +296,17 @@ class Viterbi_HMM:
         if status:
             _raise(status)
         return out[: len(database)]
+
+    def viterbi_filter(self, database: Device_database, threshold: float = 1e-3) -> dict:
+        """HMMER3's second filter stage: sequences with Viterbi Gumbel P-value <= threshold (index/score/bits/p_value)."""
+        cap = len(database)
+        index = np.empty(max(cap, 1), np.uint64)
+        score, bits, p = (np.empty(max(cap, 1), np.float32) for _ in range(3))
+        found = lib.msvh_viterbi_filter(self._h, database._h, float(threshold), cap, index.ctypes.data, score.ctypes.data,
+                                        bits.ctypes.data, p.ctypes.data)
+        if found < 0:
+            _raise(int(found))
+        return {"index": index[:found], "score": score[:found], "bits": bits[:found], "p_value": p[:found]}
 
     def __del__(self) -> None:
         if getattr(self, "_h", None):

@@ -558,3 +558,51 @@ def test_fused_gather_two_gpus(tmp_path):
     assert line["n_gpus"] == 2 and "peer_gather_unavailable" not in line, line.get("peer_gather_unavailable")
     assert line["config"]["gather"].startswith("fused into the scan kernel")
     assert line["nccl_gather"]["same_bits_as_fused_gather_on_every_rank"] is True
+
+
+# ---- speculative rows (B = N + move while J <= N) and their exact fallback ---------------------------------------------
+@pytest.mark.parametrize("name", ["100.hmm", "400.hmm", "1400.hmm", "2405.hmm"])
+def test_speculation_falls_back_exactly_on_hits(oracle, name, monkeypatch):
+    """The warp kernel assumes J <= N (no hit worth more than the entry cost) and verifies once per sequence.  Sequences
+    built from the model's consensus -- one, two or three strong segments, i.e. J far above N and re-entry through J --
+    must take the exact path; random ones must not need it; both must give the oracle's bits, with and without the
+    speculation compiled in."""
+    h = oracle.load_hmm(hmm_path(name))
+    model, table, tr3 = device_model(oracle, name)
+    leng = h["model_length"] - 1
+    consensus = np.argmax(h["match_emissions"][1:], axis=1).astype(np.uint8)
+    rng = np.random.default_rng(leng)
+    seqs = []
+    for q in range(1500):
+        kind = q % 5
+        if kind == 0:
+            seqs.append(rng.integers(0, 20, size=int(rng.integers(0, 400)), dtype=np.uint8))
+        else:
+            parts = []
+            for _ in range(kind if kind < 4 else 1):
+                a = int(rng.integers(0, max(1, leng - 8)))
+                b = int(rng.integers(a + 4, min(leng, a + 120) + 1))
+                parts += [consensus[a:b], rng.integers(0, 20, size=int(rng.integers(0, 40)), dtype=np.uint8)]
+            if kind == 4:  # a borderline hit: a short consensus stretch with mutations
+                seg = parts[0].copy()
+                seg[rng.random(seg.size) < 0.4] = rng.integers(0, 20)
+                parts[0] = seg
+            seqs.append(np.concatenate(parts))
+    for q in range(12):  # longer than the kernel is willing to speculate on (4096 rows), with and without a hit inside
+        long_one = rng.integers(0, 20, size=int(rng.integers(4090, 7000)), dtype=np.uint8)
+        if q % 2:
+            a = int(rng.integers(0, max(1, leng - 60)))
+            long_one[1000:1000 + min(60, leng - a)] = consensus[a:a + 60]
+        seqs.append(long_one)
+    codes, offsets = pack(seqs)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    assert (want > 0).mean() > 0.4  # most of these really are hits
+    db = msv.Database(codes, offsets)
+    assert ubits(db.score(model)).tolist() == ubits(want).tolist()
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+    monkeypatch.setenv("MSV_CUDA_NO_SPECULATION", "1")
+    assert ubits(db.score(model)).tolist() == ubits(want).tolist()
+    monkeypatch.delenv("MSV_CUDA_NO_SPECULATION")
+    # a database of long sequences only (mean length above the launch-level threshold) takes the exact kernel
+    long_codes, long_offsets = pack(seqs[-12:])
+    assert ubits(model.score_batch(long_codes, long_offsets)).tolist() == ubits(want[-12:]).tolist()

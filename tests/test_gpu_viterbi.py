@@ -211,9 +211,13 @@ def test_viterbi_filter_statistics(oracle):
         pv = -math.expm1(-math.exp(-lam * (b - mu)))
         assert abs(bits[q] - b) <= 1e-6 * max(1.0, abs(b))
         assert abs(p[q] - pv) <= 1e-5 * max(pv, 1e-30)
-    # the C++ class returns the same hits
+    # the C++ class reads mu / lambda from the profile and returns the same hits
     prof = msv.Profile_HMM(hmm_path(name))
     assert prof.stats_local_viterbi_mu == np.float32(mu) and prof.stats_local_viterbi_lambda == np.float32(lam)
+    hits = msv.Viterbi_HMM(prof).viterbi_filter(msv.Device_database(msv.Packed_sequences.from_arrays(codes, offsets)), 0.5)
+    keep = np.flatnonzero(p <= 0.5)
+    assert hits["index"].tolist() == keep.tolist() and ubits(hits["score"]).tolist() == ubits(want[keep]).tolist()
+    assert np.array_equal(hits["bits"], bits[keep]) and np.array_equal(hits["p_value"], p[keep])
 
 
 def test_msv_scan_two_stage_pipeline(tmp_path):
