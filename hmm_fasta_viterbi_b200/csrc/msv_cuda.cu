@@ -52,12 +52,19 @@ struct Geometry {
     Scan_kernel fn_cj_same; // tr_E_C == tr_E_J bitwise (C is J); same as fn for the generic family
     int variant = 0;        // 0: tensor-memory columns are each lane's lowest; 1: TMEM_AHEAD (they are the highest, loaded a row ahead)
     Scan_kernel fn_cj_same_exact = nullptr; // warp family: when fn_cj_same speculates B = N + move (and verifies), the kernel that never does
+    Scan_kernel fn_group_spec = nullptr;    // lane-group family (G = 8): speculative scan; failures go to a second, exact launch
     size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET) * (K - std::max(KT, 0)) * G * sizeof(float); }
 };
 
+// speculative lane-group scan: ahead of the exact one by 15 % at K = 16 (LENG 100) and 2 % at K = 28, behind it from K = 40 up
+// (profiles/r01/sweep_group_spec.txt), so it exists for the short models only
+template <int G, int K> constexpr Scan_kernel group_spec_kernel() {
+    if constexpr (G == 8 && K <= 28) return msv::msv_scan_group_spec_kernel<G, K, threads_for(K)>;
+    else return nullptr;
+}
 template <int G, int K> constexpr Geometry generic_entry() {
     return Geometry{G, K, -1, threads_for(K), msv::msv_scan_kernel<G, K, threads_for(K), false>,
-                    msv::msv_scan_kernel<G, K, threads_for(K), true>};
+                    msv::msv_scan_kernel<G, K, threads_for(K), true>, 0, nullptr, group_spec_kernel<G, K>()};
 }
 // Speculative rows (B = N + move, verified per sequence; msv_kernels.cuh) are instantiated where B200 sweeps showed them
 // ahead of the exact rows (profiles/r01/sweep_speculation*.txt: +13 % at K = 4, +2..6 % at K = 16..22 and 32..38, level at
@@ -222,6 +229,7 @@ int db_release(msv_db* db) {
     cudaFree(db->d_offsets);
     cudaFree(db->d_order);
     cudaFree(db->d_scores);
+    cudaFree(db->d_redo);
     cudaFree(db->d_stats);
     cudaFree(db->d_length_tr);
     cudaFree(db->d_hist);
@@ -272,19 +280,22 @@ int db_reserve(msv_db* db, uint64_t total, size_t n, uint64_t longest, cudaStrea
         cudaFree(db->d_offsets);
         cudaFree(db->d_order);
         cudaFree(db->d_scores);
+        cudaFree(db->d_redo);
         db->d_offsets = nullptr;
         db->d_order = nullptr;
         db->d_scores = nullptr;
+        db->d_redo = nullptr;
         db->cap_n = 0;
         const size_t cap = n + 1 + n / 8;
         MSV_CUDA_TRY(cudaMalloc(&db->d_offsets, cap * sizeof(uint64_t)));
         MSV_CUDA_TRY(cudaMalloc(&db->d_order, cap * sizeof(uint32_t)));
         MSV_CUDA_TRY(cudaMalloc(&db->d_scores, cap * sizeof(float)));
+        MSV_CUDA_TRY(cudaMalloc(&db->d_redo, cap * sizeof(uint32_t)));
         db->cap_n = cap;
     }
     if (!db->d_hist) {
         MSV_CUDA_TRY(cudaMalloc(&db->d_hist, 2 * kBuckets * sizeof(uint32_t)));
-        MSV_CUDA_TRY(cudaMalloc(&db->d_queue, kMaxChunks * sizeof(unsigned int)));
+        MSV_CUDA_TRY(cudaMalloc(&db->d_queue, 3 * kMaxChunks * sizeof(unsigned int))); // queue heads | redo counts | redo queue heads
         MSV_CUDA_TRY(cudaMalloc(&db->d_first_bad, sizeof(unsigned long long)));
     }
     if (db->h_length_tr.size() < longest + 1) {
@@ -307,7 +318,7 @@ int db_reserve(msv_db* db, uint64_t total, size_t n, uint64_t longest, cudaStrea
     }
     const unsigned long long none = ~0ull;
     MSV_CUDA_TRY(cudaMemcpyAsync(db->d_first_bad, &none, sizeof none, cudaMemcpyHostToDevice, stream));
-    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, kMaxChunks * sizeof(unsigned int), stream));
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, 3 * kMaxChunks * sizeof(unsigned int), stream));
     return MSV_OK;
 }
 
@@ -513,6 +524,28 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     if (ctas == 1) slots = std::min(slots, count); // do not launch slots that would find the queue empty
     const int threads = static_cast<int>(std::max<size_t>(32, (slots * threads_per_slot + 31) / 32 * 32));
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
+    // lane-group plan: speculative scan + exact pass over the sequences whose speculation failed (two launches; the second
+    // reads its sequence count from device memory and usually finds a handful)
+    const bool group_speculation = geo->fn_group_spec && cj_same && residues / count <= msv::kSpeculationMaxLength / 2 &&
+                                   count >= 4096 && !std::getenv("MSV_CUDA_NO_SPECULATION");
+    if (group_speculation) {
+        unsigned int* redo_count = db->d_queue + kMaxChunks + queue_slot;
+        unsigned int* redo_head = db->d_queue + 2 * kMaxChunks + queue_slot;
+        MSV_CUDA_TRY(cudaMemsetAsync(redo_count, 0, sizeof(unsigned int), stream));
+        MSV_CUDA_TRY(cudaMemsetAsync(redo_head, 0, sizeof(unsigned int), stream));
+        p.redo_list = db->d_redo + first;
+        p.redo_count = redo_count;
+        geo->fn_group_spec<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
+        ++g_launches;
+        MSV_CUDA_TRY(cudaGetLastError());
+        p.order = p.redo_list;
+        p.n_device = redo_count;
+        p.queue_head = redo_head;
+        geo->fn_cj_same<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
+        ++g_launches;
+        MSV_CUDA_TRY(cudaGetLastError());
+        return MSV_OK;
+    }
     Scan_kernel kernel = cj_same ? geo->fn_cj_same : geo->fn;
     // databases of long sequences (config 5: 10-35 k residues each) would mostly be scanned twice by the speculative rows
     const bool long_sequences = residues / count > msv::kSpeculationMaxLength / 2;
@@ -744,7 +777,7 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < plan.shared_bytes + 1024) return cudaErrorInvalidConfiguration;
         cudaError_t err = cudaMalloc(&plan.d_table, plan.table_bytes);
         if (err == cudaSuccess) err = cudaMemcpy(plan.d_table, laid.data(), plan.table_bytes, cudaMemcpyHostToDevice);
-        for (Scan_kernel fn : {geo->fn, geo->fn_cj_same, geo->fn_cj_same_exact})
+        for (Scan_kernel fn : {geo->fn, geo->fn_cj_same, geo->fn_cj_same_exact, geo->fn_group_spec})
             if (err == cudaSuccess && fn)
                 err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(plan.shared_bytes));

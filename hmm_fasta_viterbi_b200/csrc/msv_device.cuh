@@ -27,6 +27,11 @@ struct Scan_params {
     // into this GPU's address space over NVLink; already offset to this shard's first sequence).  0 = plain scan.
     uint32_t n_mirrors;
     float* mirrors[kMaxScoreMirrors];
+    // speculative lane-group scan: sequences whose speculation failed are appended here and scanned by an exact pass that
+    // takes its sequence count from device memory (n_device, when not NULL, replaces n)
+    uint32_t* redo_list;
+    unsigned int* redo_count;
+    const unsigned int* n_device;
 };
 
 // the one store per sequence: local result plus, for the fused gather, the same 4 bytes into every peer's array

@@ -50,6 +50,7 @@ struct msv_db {
     uint64_t* d_offsets = nullptr;
     uint32_t* d_order = nullptr;
     float* d_scores = nullptr;
+    uint32_t* d_redo = nullptr; // sequences a speculative lane-group scan hands to its exact pass (cap_n entries)
     float* d_stats = nullptr; // bit scores | P-values, 2 * cap_n, allocated on first use
     size_t cap_stats = 0;
     size_t cap_n = 0;

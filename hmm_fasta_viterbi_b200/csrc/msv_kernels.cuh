@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
     const uint32_t tab_lane = smem_u32(smem_raw) + gl * 16;
     const float NEG_INF = __int_as_float(0xff800000);
     const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
+    const uint32_t n_sequences = p.n_device ? *p.n_device : p.n; // the exact pass after a speculative scan reads its count here
 
     float m[K];
 #pragma unroll
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
             uint32_t ticket = 0;
             if (gl == 0) ticket = atomicAdd(p.queue_head, 1u);
             ticket = __shfl_sync(gmask, ticket, 0, G);
-            if (ticket >= p.n) {
+            if (ticket >= n_sequences) {
                 done = true;
                 buf = 0;
                 nextw = 0;
@@ -161,6 +162,154 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
             if constexpr (!CJ_SAME) C = fmaxf(C + loop, E + tEC); // MSV_HMM.cpp:108
             N = N + loop;                                         // MSV_HMM.cpp:109
             B = fmaxf(N, J) + move; // MSV_HMM.cpp:110: max(N+move, J+move) == max(N, J)+move exactly (rounding is monotone)
+        }
+    }
+}
+
+// ---- the lane-group scan with SPECULATIVE rows (see msv_scan_warp_kernel for the argument) ----------------------------
+// For short models the per-row bookkeeping of the exact row -- a group-wide max by shuffles, the J and B maxima -- costs as
+// much as the cells.  While J <= N, B is N + move and needs none of it: the row is cells + one FMNMX3 chain + this lane's
+// share of J.  Four (G = 8) sequences advance per warp instruction, four rows per residue word.  Verification is one group
+// vote when a sequence retires; a sequence that fails it is appended to `redo_list` and scanned by msv_scan_kernel in a
+// second launch that reads its count from `redo_count` (same table, same database, exact rows).  tr_E_C == tr_E_J only.
+template <int G, int K, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const Scan_params p) {
+    static_assert(G == 8 || G == 16, "lanes per sequence");
+    static_assert(K % 4 == 0 && K >= 4 && K <= kMaxColumnsPerLane, "columns per lane");
+    constexpr uint32_t ROW_BYTES = (K / 4) * G * 16;
+    constexpr uint32_t QUAD_BYTES = G * 16;
+    constexpr uint32_t COPY_CHUNK = 32768;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t table_ready;
+
+    if (p.first_bad != nullptr && *p.first_bad != ~0ull) return;
+
+    if (threadIdx.x == 0) mbarrier_init(&table_ready, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbarrier_expect_tx(&table_ready, p.table_bytes);
+        for (uint32_t at = 0; at < p.table_bytes; at += COPY_CHUNK) {
+            const uint32_t bytes = min(COPY_CHUNK, p.table_bytes - at);
+            tma_bulk_load(smem_raw + at, reinterpret_cast<const unsigned char*>(p.table) + at, bytes, &table_ready);
+        }
+    }
+    mbarrier_wait(&table_ready, 0);
+
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
+    const int left_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1)); // rotate inside the group
+    const uint32_t tab_lane = smem_u32(smem_raw) + gl * 16;
+    const float NEG_INF = __int_as_float(0xff800000);
+    const float tBMk = p.tr_B_Mk, tEJ = p.tr_E_J;
+
+    float m[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) m[j] = NEG_INF;
+    float J = NEG_INF, N = 0.0f, B = NEG_INF, loop = 0.0f, move = 0.0f; // J: this LANE's share of J
+
+    uint32_t remaining = 0, idx = 0;
+    bool active = false, done = false;
+    // residue window of the group's sequence: the next residue is byte `phase/8` of the 64-bit value (whi:wlo)
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues);
+    uint32_t wlo = 0, whi = 0, phase = 0;
+
+    auto row = [&](const uint32_t x) {
+        const uint32_t erow = tab_lane + x * ROW_BYTES;
+        const float bt = B + tBMk;
+        const float left = __shfl_sync(0xffffffffu, m[K - 1], left_lane);
+        float e = NEG_INF;
+#pragma unroll
+        for (int q = K / 4 - 1; q >= 0; --q) {
+            const float4 ev = lds128(erow + q * QUAD_BYTES);
+            const int j = 4 * q;
+            m[j + 3] = ev.w + fmaxf(m[j + 2], bt);
+            m[j + 2] = ev.z + fmaxf(m[j + 1], bt);
+            m[j + 1] = ev.y + fmaxf(m[j], bt);
+            m[j] = ev.x + fmaxf(q ? m[j > 0 ? j - 1 : 0] : left, bt);
+            e = fmaxf(fmaxf(e, m[j + 3]), m[j + 2]);
+            e = fmaxf(fmaxf(e, m[j + 1]), m[j]);
+        }
+        J = fmaxf(J + loop, e + tEJ);
+        N = N + loop;
+        B = N + move; // = max(N, J) + move while J <= N -- verified when the sequence retires
+    };
+
+    for (;;) {
+        // ---- retire finished sequences, pull new ones (group-uniform control flow) ----
+        while (remaining == 0 && !done) {
+            if (active) {
+                // if J overtook N at any row, this lane's or a neighbour's share still is >= N now (both decay by + loop)
+                const bool suspect = __any_sync(gmask, J >= N);
+                float best = J;
+#pragma unroll
+                for (int d = G / 2; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(gmask, best, d));
+                if (gl == 0) {
+                    if (suspect) p.redo_list[atomicAdd(p.redo_count, 1u)] = idx;
+                    else store_score(p, idx, best + move);
+                }
+                active = false;
+            }
+            uint32_t ticket = 0;
+            if (gl == 0) ticket = atomicAdd(p.queue_head, 1u);
+            ticket = __shfl_sync(gmask, ticket, 0, G);
+            if (ticket >= p.n) {
+                done = true;
+                wp = reinterpret_cast<const uint32_t*>(p.residues); // finished groups keep executing rows on harmless input
+                wlo = whi = phase = 0;
+                break;
+            }
+            idx = __ldg(p.order + ticket);
+            const uint64_t begin = __ldg(p.offsets + idx);
+            const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
+            const float2 tr = __ldg(p.length_tr + len);
+            loop = tr.x;
+            move = tr.y;
+#pragma unroll
+            for (int j = 0; j < K; ++j) m[j] = NEG_INF;
+            J = NEG_INF;
+            N = 0.0f;
+            B = move;
+            const uint32_t mis = static_cast<uint32_t>(begin) & 3u;
+            wp = reinterpret_cast<const uint32_t*>(p.residues + (begin - mis));
+            wlo = __ldg(wp);
+            whi = __ldg(wp + 1);
+            wp += 2;
+            phase = 8u * mis;
+            remaining = len;
+            active = true;
+        }
+
+        // ---- rows that every group of this warp can run without anyone finishing: warp-uniform trip count ----
+        const uint32_t mine = done ? 0xffffffffu : remaining;
+        const uint32_t steps = __reduce_min_sync(0xffffffffu, mine);
+        if (steps == 0xffffffffu) break;
+        if (!done) remaining -= steps;
+        const uint32_t advance = done ? 0u : 1u;
+
+#pragma unroll 1
+        for (uint32_t t = steps >> 2; t > 0; --t) { // one residue word = four rows
+            const uint32_t word = __funnelshift_r(wlo, whi, phase);
+            wlo = whi;
+            whi = __ldg(wp);
+            wp += advance;
+            row(word & 0xffu);
+            row((word >> 8) & 0xffu);
+            row((word >> 16) & 0xffu);
+            row(word >> 24);
+        }
+#pragma unroll 1
+        for (uint32_t t = steps & 3u; t > 0; --t) {
+            const uint32_t x = __funnelshift_r(wlo, whi, phase) & 0xffu;
+            phase += 8u;
+            if (phase == 32u) {
+                phase = 0;
+                wlo = whi;
+                whi = __ldg(wp);
+                wp += advance;
+            }
+            row(x);
         }
     }
 }

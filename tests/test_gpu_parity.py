@@ -606,3 +606,38 @@ def test_speculation_falls_back_exactly_on_hits(oracle, name, monkeypatch):
     # a database of long sequences only (mean length above the launch-level threshold) takes the exact kernel
     long_codes, long_offsets = pack(seqs[-12:])
     assert ubits(model.score_batch(long_codes, long_offsets)).tolist() == ubits(want[-12:]).tolist()
+
+
+@pytest.mark.parametrize("name,geometry", [("100.hmm", "8,16"), ("200.hmm", "8,28")])
+def test_group_speculation_and_its_exact_pass(oracle, name, geometry, monkeypatch):
+    """Eight lanes per sequence, speculative rows: sequences whose speculation fails (consensus-derived hits) are appended
+    to a list on the device and scanned by a second, exact launch that reads its count from device memory."""
+    monkeypatch.setenv("MSV_CUDA_GEOMETRY", geometry)
+    h = oracle.load_hmm(hmm_path(name))
+    model, table, tr3 = device_model(oracle, name)
+    assert model.geometry["lanes_per_sequence"] == 8
+    leng = h["model_length"] - 1
+    consensus = np.argmax(h["match_emissions"][1:], axis=1).astype(np.uint8)
+    rng = np.random.default_rng(leng + 1)
+    seqs = []
+    for q in range(6000):  # >= 4096 sequences: below that the launch does not speculate
+        if q % 3 == 0:
+            a = int(rng.integers(0, leng - 20))
+            b = int(rng.integers(a + 10, min(leng, a + 90) + 1))
+            seqs.append(np.concatenate([rng.integers(0, 20, size=int(rng.integers(0, 30)), dtype=np.uint8), consensus[a:b],
+                                        rng.integers(0, 20, size=int(rng.integers(0, 30)), dtype=np.uint8)]))
+        else:
+            seqs.append(rng.integers(0, 20, size=int(rng.integers(0, 350)), dtype=np.uint8))
+    codes, offsets = pack(seqs)
+    want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+    assert 0.2 < (want > 0).mean() < 0.5
+    db = msv.Database(codes, offsets)
+    _cabi.launch_count(reset=True)
+    assert ubits(db.score(model)).tolist() == ubits(want).tolist()
+    assert _cabi.launch_count() == 2  # speculative scan + exact pass
+    assert ubits(db.score(model)).tolist() == ubits(want).tolist()  # counters are reset between scans
+    assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
+    monkeypatch.setenv("MSV_CUDA_NO_SPECULATION", "1")
+    _cabi.launch_count(reset=True)
+    assert ubits(db.score(model)).tolist() == ubits(want).tolist()
+    assert _cabi.launch_count() == 1
