@@ -111,6 +111,13 @@ template <int K, int KT, int T> constexpr Geometry warp_entry_ahead() {
 #define MSV_FOR_EACH_K_FROM_28(X, A)                                                                                   \
     X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) X(A, 76)  \
     X(A, 80) X(A, 84) X(A, 88)
+#ifdef MSV_QUICK_BUILD // development aid: only what a 1400-column model needs, so that a kernel experiment compiles in seconds
+const Geometry g_geometries[] = {generic_entry<32, 44>(), warp_entry_ahead<44, 24, 512>(), warp_entry<44, 16>(), quad_entry<12, 8>()
+#ifdef MSV_QUICK_EXTRA
+                                 , MSV_QUICK_EXTRA
+#endif
+};
+#else
 const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(MSV_GENERIC, 16) MSV_FOR_EACH_K(MSV_GENERIC, 32)
                                      MSV_WARP(0, 4) MSV_WARP(0, 8) MSV_WARP(8, 8) MSV_WARP(8, 12) MSV_WARP(8, 16) MSV_WARP(8, 20)
                                          MSV_WARP(16, 16) MSV_WARP(16, 20) MSV_WARP(24, 24) MSV_FOR_EACH_K_FROM_24(MSV_WARP, 16)
@@ -126,6 +133,7 @@ const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(M
                                  quad_entry<4, 0>(), quad_entry<8, 8>(), quad_entry<12, 8>(), quad_entry<16, 16>(), quad_entry<20, 16>(),
                                  quad_entry<24, 16>(), quad_entry<28, 16>(), quad_entry<32, 16>(), quad_entry<36, 16>(),
                                  quad_entry<40, 24>(), quad_entry<44, 24>()};
+#endif
 
 const Geometry* find_geometry(int G, int K, int KT, int threads = 0, int variant = 0) {
     for (const auto& g : g_geometries)

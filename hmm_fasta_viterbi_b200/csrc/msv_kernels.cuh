@@ -516,7 +516,11 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         // instruction scheduler's luck -- and the longest bodies stop fitting the instruction cache (-10 % at K = 76).
         constexpr bool EIGHT_ROWS = K == 20 || K == 30 || K == 32 || K == 36 || K == 42 || K == 44 || K == 52 || K == 54 || K == 58 ||
                                     K == 60 || K == 68;
+#ifdef MSV_FORCE_UNROLL // development aid (with MSV_QUICK_BUILD)
+        constexpr int WORD_UNROLL = MSV_FORCE_UNROLL;
+#else
         constexpr int WORD_UNROLL = K == 4 ? 4 : EIGHT_ROWS ? 2 : 1;
+#endif
 #pragma unroll WORD_UNROLL
         for (uint32_t i = 0; i < quads; ++i) {
             const uint32_t ahead = __funnelshift_r(w1, w2, shift);
