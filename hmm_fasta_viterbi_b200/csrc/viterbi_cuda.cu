@@ -16,7 +16,7 @@ namespace {
 using Scan_kernel = void (*)(const msv::Scan_params);
 struct Viterbi_geometry {
     int K, threads;
-    Scan_kernel fn, fn_cj_same;
+    Scan_kernel fn, fn_cj_same, fn_cj_same_spec; // general, tr_E_C == tr_E_J, the latter with speculative rows
     size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 * sizeof(float); }
     size_t table_floats() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 + 32 * 5 * static_cast<size_t>(K) + 32 * 8; }
 };
@@ -25,7 +25,8 @@ struct Viterbi_geometry {
 constexpr int viterbi_threads_for(int K) { return K <= 8 ? 768 : K <= 16 ? 512 : K <= 24 ? 384 : K <= 56 ? 256 : 224; }
 template <int K> constexpr Viterbi_geometry viterbi_entry() {
     return Viterbi_geometry{K, viterbi_threads_for(K), msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), false>,
-                            msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), true>};
+                            msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), true>,
+                            msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), true, true>};
 }
 const Viterbi_geometry k_viterbi_geometries[] = {
     viterbi_entry<4>(),  viterbi_entry<8>(),  viterbi_entry<12>(), viterbi_entry<16>(), viterbi_entry<20>(),
@@ -138,7 +139,7 @@ int msv_cuda_viterbi_model_create(const float* emission_scores, const float* log
     model->sm_count = prop.multiProcessorCount;
     cudaError_t err = cudaMalloc(&model->d_table, laid.size() * sizeof(float));
     if (err == cudaSuccess) err = cudaMemcpy(model->d_table, laid.data(), laid.size() * sizeof(float), cudaMemcpyHostToDevice);
-    for (Scan_kernel fn : {geo->fn, geo->fn_cj_same})
+    for (Scan_kernel fn : {geo->fn, geo->fn_cj_same, geo->fn_cj_same_spec})
         if (err == cudaSuccess)
             err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(geo->shared_bytes()));
@@ -202,7 +203,10 @@ int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scor
     const size_t ctas = std::max<size_t>(1, std::min<size_t>(model->sm_count, (db->n + warps_per_cta - 1) / warps_per_cta));
     const size_t warps = ctas == 1 ? std::min(warps_per_cta, db->n) : std::min(warps_per_cta, (db->n + ctas - 1) / ctas);
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
-    (cj_same ? geo->fn_cj_same : geo->fn)<<<static_cast<int>(ctas), static_cast<int>(warps * 32), geo->shared_bytes(), stream>>>(p);
+    // speculative rows unless the database is one of long sequences, which would mostly be scanned twice
+    const bool speculate = db->total / db->n <= msv::kViterbiSpeculationMaxLength / 2 && !std::getenv("MSV_CUDA_NO_SPECULATION");
+    const Scan_kernel kernel = !cj_same ? geo->fn : speculate ? geo->fn_cj_same_spec : geo->fn_cj_same;
+    kernel<<<static_cast<int>(ctas), static_cast<int>(warps * 32), geo->shared_bytes(), stream>>>(p);
     msv_detail::count_launch();
     MSV_CUDA_TRY(cudaGetLastError());
     return MSV_OK;

@@ -40,10 +40,13 @@
 //     columns), staged once per CTA by the TMA unit.
 #pragma once
 
+#include <type_traits>
+
 #include "msv_device.cuh"
 
 namespace msv {
 
+constexpr uint32_t kViterbiSpeculationMaxLength = 4096;
 constexpr int kViterbiMaxColumnsPerLane = 80; // 22 * K * 128 B of shared memory
 
 // Table in global memory (floats), K columns per lane, Q = K / 4; every transition belongs to the column it leaves:
@@ -53,8 +56,12 @@ constexpr int kViterbiMaxColumnsPerLane = 80; // 22 * K * 128 B of shared memory
 //   [.., + 32*5*K)                tensor-memory part     [lane][q][tMM x4 | tIM x4 | tDM x4 | tMI x4 | tII x4]
 //   [.., + 32*8)                  per lane: tMM, tIM, tDM, tMD, tDD of the lane's LAST slot (what it hands to the right; -inf
 //                                 for lane 31), 3 unused words
-template <int K, int THREADS, bool CJ_SAME>
+// SPECULATE (tr_E_C == tr_E_J only): as in the MSV warp kernel, B[i] = max(N[i], J[i]) + move is N[i] + move while J <= N, so
+// the row needs no warp-wide E: each lane carries its share j = max(j + loop, E_lane + tEJ), one vote per sequence checks
+// "no lane ends with j >= N", and a sequence that fails it is scanned again with the exact row.  Same bits.
+template <int K, int THREADS, bool CJ_SAME, bool SPECULATE = false>
 __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Scan_params p) {
+    constexpr bool SPEC = SPECULATE && CJ_SAME;
     static_assert(K % 4 == 0 && K >= 4 && K <= kViterbiMaxColumnsPerLane, "columns per lane");
     constexpr int Q = K / 4;
     constexpr uint32_t ROW_BYTES = K * 32 * 4; // one residue's emissions; also the size of the tMD and of the tDD block
@@ -128,15 +135,13 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
         const float loop = tr.x, move = tr.y;
 
         float m[K], in[K], d[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) m[j] = in[j] = d[j] = NEG_INF;
-        float J = NEG_INF, C = NEG_INF, N = 0.0f, B = move;
+        float J, C, N, B;
 
         // transitions of the column group at hand / of the next one (tensor memory, double buffered across the unrolled loop)
         float tq[2][20];
-        tmem_load<20>(tmem_lane_base, tq[0]);
 
-        auto row = [&](const uint32_t x) {
+        auto row = [&](auto exact_tag, const uint32_t x) {
+            constexpr bool EXACT = decltype(exact_tag)::value;
             const uint32_t erow = tab_lane + x * ROW_BYTES;
             const float bt = B + tBMk;
             // what the first slot of the lane to the right receives from this lane's last slot (previous row); lane 31's
@@ -199,32 +204,52 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
                 if (!crossed) break;
             }
             if (lane == 31) e = fmaxf(e, d[K - 1]); // D[LENG] -> E
-            float E;
-            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(E) : "f"(e));
-            J = fmaxf(J + loop, E + tEJ);
-            if constexpr (!CJ_SAME) C = fmaxf(C + loop, E + tEC);
-            N = N + loop;
-            B = fmaxf(N, J) + move;
+            if constexpr (EXACT) {
+                float E;
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(E) : "f"(e));
+                J = fmaxf(J + loop, E + tEJ);
+                if constexpr (!CJ_SAME) C = fmaxf(C + loop, E + tEC);
+                N = N + loop;
+                B = fmaxf(N, J) + move;
+            } else {
+                J = fmaxf(J + loop, e + tEJ); // this lane's share of J
+                N = N + loop;
+                B = N + move;                 // = max(N, J) + move while J <= N; verified after the last row
+            }
         };
 
-        // residues arrive as aligned 32-bit words; a funnel shift undoes the byte misalignment of the sequence start
-        const uint32_t shift = (static_cast<uint32_t>(begin) & 3u) * 8u;
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues + (begin & ~static_cast<uint64_t>(3)));
-        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
-        wp += 2;
-        uint32_t word = __funnelshift_r(w0, w1, shift);
+        // one pass over the sequence with the given kind of row.  Residues arrive as aligned 32-bit words; a funnel shift
+        // undoes the byte misalignment of the sequence start.
+        auto scan = [&](auto exact_tag) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) m[j] = in[j] = d[j] = NEG_INF;
+            J = NEG_INF, C = NEG_INF, N = 0.0f, B = move;
+            tmem_load<20>(tmem_lane_base, tq[0]);
+            const uint32_t shift = (static_cast<uint32_t>(begin) & 3u) * 8u;
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues + (begin & ~static_cast<uint64_t>(3)));
+            uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
+            wp += 2;
+            uint32_t word = __funnelshift_r(w0, w1, shift);
 #pragma unroll 1
-        for (uint32_t i = 0; i < len; ++i) {
-            row(word & 0xffu);
-            word >>= 8;
-            if ((i & 3u) == 3u) {
-                w0 = w1;
-                w1 = __ldg(wp);
-                ++wp;
-                word = __funnelshift_r(w0, w1, shift);
+            for (uint32_t i = 0; i < len; ++i) {
+                row(exact_tag, word & 0xffu);
+                word >>= 8;
+                if ((i & 3u) == 3u) {
+                    w0 = w1;
+                    w1 = __ldg(wp);
+                    ++wp;
+                    word = __funnelshift_r(w0, w1, shift);
+                }
             }
+            tmem_wait<20>(tq[0]); // retire the group that was requested for a row that does not exist
+        };
+        if (SPEC && len <= kViterbiSpeculationMaxLength) {
+            scan(std::bool_constant<!SPEC>{});
+            if (__any_sync(0xffffffffu, J >= N)) scan(std::bool_constant<true>{}); // J may have overtaken N: exact rows
+            else asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(J) : "f"(J));
+        } else {
+            scan(std::bool_constant<true>{});
         }
-        tmem_wait<20>(tq[0]); // retire the group that was requested for a row that does not exist
         if (lane == 0) store_score(p, idx, (CJ_SAME ? J : C) + move);
     }
 

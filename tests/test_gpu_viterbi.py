@@ -168,6 +168,31 @@ def test_edge_cases_and_errors(oracle):
     assert err.value.status == -5
 
 
+def test_speculative_rows_equal_exact_rows(oracle, monkeypatch):
+    """The kernel assumes J <= N (B = N + move) and verifies once per sequence; hits (consensus-derived sequences) must be
+    rescanned exactly, random sequences not; both kernels must return the oracle's bits."""
+    h = oracle.load_hmm(hmm_path("700.hmm"))
+    model, table, logtr, tr3 = viterbi_model(oracle, h["match_emissions"], h["transitions"])
+    consensus = np.argmax(h["match_emissions"][1:], axis=1).astype(np.uint8)
+    rng = np.random.default_rng(70)
+    seqs = []
+    for q in range(600):
+        if q % 2:
+            a = int(rng.integers(0, 600))
+            seqs.append(np.concatenate([rng.integers(0, 20, size=20, dtype=np.uint8), consensus[a:a + int(rng.integers(8, 90))],
+                                        rng.integers(0, 20, size=int(rng.integers(0, 50)), dtype=np.uint8)]))
+        else:
+            seqs.append(rng.integers(0, 20, size=int(rng.integers(0, 400)), dtype=np.uint8))
+    seqs.append(rng.integers(0, 20, size=5000, dtype=np.uint8))  # longer than the kernel speculates on
+    codes, offsets = pack(seqs)
+    want = oracle.viterbi_score_batch(table, logtr, tr3, codes, offsets, threads=CORES)
+    assert 0.3 < (want > 0).mean() < 0.6
+    db = msv.Database(codes, offsets)
+    assert ubits(db.viterbi(model)).tolist() == ubits(want).tolist()
+    monkeypatch.setenv("MSV_CUDA_NO_SPECULATION", "1")
+    assert ubits(db.viterbi(model)).tolist() == ubits(want).tolist()
+
+
 def test_full_size_properties(oracle):
     """1400.hmm x 20 000 Swiss-Prot-like sequences: run-to-run bit determinism, a seeded sample against the oracle, and
     invariance under permutation of the database (scores belong to sequences, not to queue positions)."""
