@@ -21,8 +21,10 @@ struct Viterbi_geometry {
     size_t table_floats() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 + 32 * 5 * static_cast<size_t>(K) + 32 * 8; }
 };
 
-// three state registers per column: the register file, not shared memory, bounds the warps per SM
-constexpr int viterbi_threads_for(int K) { return K <= 8 ? 768 : K <= 16 ? 512 : K <= 24 ? 384 : K <= 56 ? 256 : 224; }
+// three state registers per column: the register file, not shared memory, bounds the warps per SM.  Registers are handed
+// out to a CTA in units of four warps, so only multiples of 128 threads are worth considering: 768 / 512 / 384 / 256 threads
+// leave 80 / 128 / 168 / 255 registers each; the kernel wants 76, 108, 118, 126, 141, 154, 164, 176, ... at K = 4, 8, ... 32.
+constexpr int viterbi_threads_for(int K) { return K <= 4 ? 768 : K <= 16 ? 512 : K <= 28 ? 384 : 256; }
 template <int K> constexpr Viterbi_geometry viterbi_entry() {
     return Viterbi_geometry{K, viterbi_threads_for(K), msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), false>,
                             msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), true>,

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
     const float edge_dd = __ldg(tensor_src + 32 * TENSOR_WORDS + 8 * lane + 4);
     const uint32_t tab_lane = smem_u32(smem_raw) + lane * 16;
     const uint32_t md_lane = tab_lane + EMISSION_BYTES, dd_lane = md_lane + ROW_BYTES;
+    const float4 dd_first = lds128(dd_lane); // tDD of this lane's first four slots, kept in registers
     const int left_lane = (lane + 31) & 31;
     const float NEG_INF = __int_as_float(0xff800000);
     const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
@@ -177,21 +178,30 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
                 if (q == Q - 1) tmem_load<20>(tmem_lane_base, tq[0]);
             }
             // ---- delete paths that arrive from the lane to the left ----
+            // The first four columns are done unconditionally with tDD from registers (the carried-in path nearly always
+            // improves them): no vote, no shared-memory load on this serial stretch.  Further groups only while a vote says
+            // the path is still alive somewhere; the hand-over repeats only if some lane's last column changed.
             for (;;) {
+                const float last_before = d[K - 1];
                 const float c_out = fmaxf(m[K - 1] + edge.w, d[K - 1] + edge_dd); // D of the right neighbour's first slot
                 float carried = __shfl_sync(0xffffffffu, c_out, left_lane);       // lane 0 receives lane 31's -inf
-                if (!__any_sync(0xffffffffu, carried > d[0])) break;
+                d[0] = fmaxf(d[0], carried);
+                carried = carried + dd_first.x;
+                d[1] = fmaxf(d[1], carried);
+                carried = carried + dd_first.y;
+                d[2] = fmaxf(d[2], carried);
+                carried = carried + dd_first.z;
+                d[3] = fmaxf(d[3], carried);
+                carried = carried + dd_first.w;
                 bool crossed = true; // a carried path is still alive after the last column of some lane
 #pragma unroll
-                for (int q = 0; q < Q; ++q) {
+                for (int q = 1; q < Q; ++q) {
                     const int j = 4 * q;
-                    const float4 dd = lds128_volatile(dd_lane + q * 512);
-                    if (q > 0) {
-                        if (!__any_sync(0xffffffffu, carried > d[j])) { // dead everywhere: nothing further can change
-                            crossed = false;
-                            break;
-                        }
+                    if (!__any_sync(0xffffffffu, carried > d[j])) { // dead everywhere: nothing further can change
+                        crossed = false;
+                        break;
                     }
+                    const float4 dd = lds128_volatile(dd_lane + q * 512);
                     d[j] = fmaxf(d[j], carried);
                     carried = carried + dd.x;
                     d[j + 1] = fmaxf(d[j + 1], carried);
@@ -201,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
                     d[j + 3] = fmaxf(d[j + 3], carried);
                     carried = carried + dd.w;
                 }
-                if (!crossed) break;
+                if (!crossed || !__any_sync(0xffffffffu, d[K - 1] > last_before)) break;
             }
             if (lane == 31) e = fmaxf(e, d[K - 1]); // D[LENG] -> E
             if constexpr (EXACT) {
