@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
             const float left = __shfl_sync(0xffffffffu, m[K - 1], left_lane);
             float e = NEG_INF;
             // columns are updated from the highest down; TB / SB = first column served by tensor / shared memory
-            constexpr int TB = AHEAD ? KS : 0, SB = AHEAD ? 0 : KT;
+            [[maybe_unused]] constexpr int TB = AHEAD ? KS : 0, SB = AHEAD ? 0 : KT;
             const auto tensor_columns = [&] {
                 if constexpr (KT > 0) {
                     tmem_wait<KT>(te);

@@ -23,8 +23,9 @@ struct Viterbi_geometry {
 
 // three state registers per column: the register file, not shared memory, bounds the warps per SM.  Registers are handed
 // out to a CTA in units of four warps, so only multiples of 128 threads are worth considering: 768 / 512 / 384 / 256 threads
-// leave 80 / 128 / 168 / 255 registers each; the kernel wants 76, 108, 118, 126, 141, 154, 164, 176, ... at K = 4, 8, ... 32.
-constexpr int viterbi_threads_for(int K) { return K <= 4 ? 768 : K <= 16 ? 512 : K <= 28 ? 384 : 256; }
+// leave 80 / 128 / 168 / 255 registers each; the kernel wants 76, 108, 118, 126, 141, 154, 164, 176, 187, 200 ... at K = 4, 8, ... 40
+// (and is content with 158 / 168 at K = 32 / 36 when that is the budget).
+constexpr int viterbi_threads_for(int K) { return K <= 4 ? 768 : K <= 16 ? 512 : K <= 36 ? 384 : 256; }
 template <int K> constexpr Viterbi_geometry viterbi_entry() {
     return Viterbi_geometry{K, viterbi_threads_for(K), msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), false>,
                             msv::viterbi_scan_warp_kernel<K, viterbi_threads_for(K), true>,

@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
         const float2 tr = __ldg(p.length_tr + len);
         const float loop = tr.x, move = tr.y;
 
-        float m[K], in[K], d[K];
-        float J, C, N, B;
+        float m[K] = {}, in[K] = {}, d[K] = {}; // (set by scan() below before any row reads them)
+        float J = 0.0f, C = 0.0f, N = 0.0f, B = 0.0f;
 
         // transitions of the column group at hand / of the next one (tensor memory, double buffered across the unrolled loop)
         float tq[2][20];
