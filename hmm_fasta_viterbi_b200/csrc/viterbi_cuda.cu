@@ -17,8 +17,9 @@ using Scan_kernel = void (*)(const msv::Scan_params);
 struct Viterbi_geometry {
     int K, threads;
     Scan_kernel fn, fn_cj_same, fn_cj_same_spec; // general, tr_E_C == tr_E_J, the latter with speculative rows
-    size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 * sizeof(float); }
-    size_t table_floats() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * 32 + 32 * 5 * static_cast<size_t>(K) + 32 * 8; }
+    int G = 32;                                  // lanes per sequence: 32 (one warp) or 8 (four sequences per warp, short models)
+    size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * G * sizeof(float); }
+    size_t table_floats() const { return static_cast<size_t>(MSV_ALPHABET + 2) * K * G + 32 * 5 * static_cast<size_t>(K) + 32 * 8; }
 };
 
 // three state registers per column: the register file, not shared memory, bounds the warps per SM.  Registers are handed
@@ -38,6 +39,24 @@ const Viterbi_geometry k_viterbi_geometries[] = {
     viterbi_entry<64>(), viterbi_entry<68>(), viterbi_entry<72>(), viterbi_entry<76>(), viterbi_entry<80>(),
 };
 
+// eight lanes per sequence (viterbi_scan_group_kernel), exact rows only
+constexpr int viterbi_group_threads_for(int K) { return K <= 12 ? 512 : K <= 28 ? 384 : 256; } // 118 ... 167, 207 ... 254 registers
+template <int K> constexpr Viterbi_geometry viterbi_group_entry() {
+    return Viterbi_geometry{K, viterbi_group_threads_for(K), msv::viterbi_scan_group_kernel<8, K, viterbi_group_threads_for(K), false>,
+                            msv::viterbi_scan_group_kernel<8, K, viterbi_group_threads_for(K), true>,
+                            msv::viterbi_scan_group_kernel<8, K, viterbi_group_threads_for(K), true>, 8};
+}
+const Viterbi_geometry k_viterbi_group_geometries[] = {
+    viterbi_group_entry<8>(),  viterbi_group_entry<12>(), viterbi_group_entry<16>(), viterbi_group_entry<20>(), viterbi_group_entry<24>(),
+    viterbi_group_entry<28>(), viterbi_group_entry<32>(), viterbi_group_entry<36>(), viterbi_group_entry<40>(), viterbi_group_entry<44>(),
+    viterbi_group_entry<48>(), viterbi_group_entry<52>(), viterbi_group_entry<56>(),
+};
+const Viterbi_geometry* choose_viterbi_group_geometry(size_t model_length) {
+    for (const Viterbi_geometry& g : k_viterbi_group_geometries)
+        if (static_cast<size_t>(g.K) * 8 >= model_length) return &g;
+    return nullptr;
+}
+
 const Viterbi_geometry* choose_viterbi_geometry(size_t model_length) {
     // 32 * K slots hold columns 0 .. LENG (column 0 is the dummy the recurrence needs at its left end)
     for (const Viterbi_geometry& g : k_viterbi_geometries)
@@ -50,8 +69,10 @@ const Viterbi_geometry* choose_viterbi_geometry(size_t model_length) {
 struct msv_viterbi_model {
     int device = 0;
     size_t model_length = 0;
-    const Viterbi_geometry* geo = nullptr;
+    const Viterbi_geometry* geo = nullptr; // one warp per sequence
     float4* d_table = nullptr;
+    const Viterbi_geometry* group_geo = nullptr; // eight lanes per sequence: short models, when there are sequences enough
+    float4* d_group_table = nullptr;
     float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
     int sm_count = 0;
     msv_db* workspace = nullptr; // reused by msv_cuda_viterbi_batch (grow-only buffers)
@@ -92,44 +113,56 @@ int msv_cuda_viterbi_model_create(const float* emission_scores, const float* log
     if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < geo->shared_bytes() + 1024)
         return fail(MSV_ERR_MODEL_TOO_LONG, "Viterbi: tables of a %zu-column model exceed shared memory", model_length - 1);
 
-    // kernel layout, see viterbi_kernels.cuh.  Slot s = lane * K + j holds model column s - pad (right aligned).
-    const int K = geo->K;
+    // kernel layout, see viterbi_kernels.cuh.  A sequence occupies G lanes (32, or 8 in the lane-group kernel); slot
+    // s = lane * K + j holds model column s - pad (right aligned).
     const long columns = static_cast<long>(model_length) - 1; // LENG
-    const long pad = 32L * K - 1 - columns;
     const float ninf = -std::numeric_limits<float>::infinity();
     enum { MM = 0, MI = 1, MD = 2, IM = 3, II = 4, DM = 5, DD = 6 }; // order of Profile_HMM::transitions (Profile_HMM.hpp:29)
     const auto tr = [&](long node, int which) { return log_transitions[node * MSV_TRANSITIONS + which]; };
-    // every transition is stored with the column it leaves; columns 1 .. LENG-1 have successors, nothing else does
-    const auto own = [&](long slot, int which) {
-        const long c = slot - pad;
-        return (c >= 1 && c <= columns - 1) ? tr(c, which) : ninf;
-    };
-    std::vector<float> laid(geo->table_floats(), ninf);
-    const size_t row = static_cast<size_t>(K) * 32;
-    float* md = laid.data() + MSV_ALPHABET * row;
-    float* dd = md + row;
-    float* tensor = dd + row;
-    float* edge = tensor + 32 * 5 * static_cast<size_t>(K);
-    for (int lane = 0; lane < 32; ++lane) {
-        for (int j = 0; j < K; ++j) {
-            const long slot = static_cast<long>(lane) * K + j, c = slot - pad;
-            const int q = j / 4, w = j % 4;
-            const size_t at = (static_cast<size_t>(q) * 32 + lane) * 4 + w;
-            for (int res = 0; res < MSV_ALPHABET; ++res)
-                laid[res * row + at] = (c >= 1 && c <= columns) ? emission_scores[res * model_length + c] : ninf;
-            md[at] = own(slot, MD);
-            dd[at] = own(slot, DD);
-            float* t = tensor + (static_cast<size_t>(lane) * (K / 4) + q) * 20;
-            t[w] = own(slot, MM);
-            t[4 + w] = own(slot, IM);
-            t[8 + w] = own(slot, DM);
-            t[12 + w] = own(slot, MI);
-            t[16 + w] = own(slot, II);
+    const auto upload = [&](const Viterbi_geometry* g, float4** d_table) -> cudaError_t {
+        const int K = g->K, G = g->G;
+        const long pad = static_cast<long>(G) * K - 1 - columns;
+        // every transition is stored with the column it leaves; columns 1 .. LENG-1 have successors, nothing else does
+        const auto own = [&](long slot, int which) {
+            const long c = slot - pad;
+            return (c >= 1 && c <= columns - 1) ? tr(c, which) : ninf;
+        };
+        std::vector<float> laid(g->table_floats(), ninf);
+        const size_t row = static_cast<size_t>(K) * G;
+        float* md = laid.data() + MSV_ALPHABET * row;
+        float* dd = md + row;
+        float* tensor = dd + row;
+        float* edge = tensor + 32 * 5 * static_cast<size_t>(K);
+        for (int lane = 0; lane < G; ++lane) {
+            for (int j = 0; j < K; ++j) {
+                const long slot = static_cast<long>(lane) * K + j, c = slot - pad;
+                const int q = j / 4, w = j % 4;
+                const size_t at = (static_cast<size_t>(q) * G + lane) * 4 + w;
+                for (int res = 0; res < MSV_ALPHABET; ++res)
+                    laid[res * row + at] = (c >= 1 && c <= columns) ? emission_scores[res * model_length + c] : ninf;
+                md[at] = own(slot, MD);
+                dd[at] = own(slot, DD);
+                for (int copy = lane; copy < 32; copy += G) { // the tensor-memory part covers all 32 lanes of a warp
+                    float* t = tensor + (static_cast<size_t>(copy) * (K / 4) + q) * 20;
+                    t[w] = own(slot, MM);
+                    t[4 + w] = own(slot, IM);
+                    t[8 + w] = own(slot, DM);
+                    t[12 + w] = own(slot, MI);
+                    t[16 + w] = own(slot, II);
+                }
+            }
+            const long last = static_cast<long>(lane) * K + K - 1; // the last lane: column LENG, which has no successor
+            const int which[5] = {MM, IM, DM, MD, DD};
+            for (int i = 0; i < 5; ++i) edge[lane * 8 + i] = own(last, which[i]);
         }
-        const long last = static_cast<long>(lane) * K + K - 1; // lane 31: column LENG, which has no successor
-        const int which[5] = {MM, IM, DM, MD, DD};
-        for (int i = 0; i < 5; ++i) edge[lane * 8 + i] = own(last, which[i]);
-    }
+        cudaError_t err = cudaMalloc(d_table, laid.size() * sizeof(float));
+        if (err == cudaSuccess) err = cudaMemcpy(*d_table, laid.data(), laid.size() * sizeof(float), cudaMemcpyHostToDevice);
+        for (Scan_kernel fn : {g->fn, g->fn_cj_same, g->fn_cj_same_spec})
+            if (err == cudaSuccess)
+                err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(g->shared_bytes()));
+        return err;
+    };
 
     auto* model = new (std::nothrow) msv_viterbi_model();
     if (!model) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
@@ -140,18 +173,24 @@ int msv_cuda_viterbi_model_create(const float* emission_scores, const float* log
     model->tr_E_C = tr_E_C;
     model->tr_E_J = tr_E_J;
     model->sm_count = prop.multiProcessorCount;
-    cudaError_t err = cudaMalloc(&model->d_table, laid.size() * sizeof(float));
-    if (err == cudaSuccess) err = cudaMemcpy(model->d_table, laid.data(), laid.size() * sizeof(float), cudaMemcpyHostToDevice);
-    for (Scan_kernel fn : {geo->fn, geo->fn_cj_same, geo->fn_cj_same_spec})
-        if (err == cudaSuccess)
-            err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(geo->shared_bytes()));
+    const cudaError_t err = upload(geo, &model->d_table);
     if (err != cudaSuccess) {
         cudaFree(model->d_table);
         delete model;
         (void)cudaGetLastError();
         return fail(err == cudaErrorMemoryAllocation ? MSV_ERR_OUT_OF_MEMORY : MSV_ERR_CUDA, "Viterbi model upload failed: %s",
                     cudaGetErrorString(err));
+    }
+    // the lane-group plan is optional: short models only, and a failure to set it up just leaves the warp plan
+    if (const Viterbi_geometry* group = choose_viterbi_group_geometry(model_length)) {
+        if (static_cast<size_t>(prop.sharedMemPerBlockOptin) >= group->shared_bytes() + 1024 &&
+            upload(group, &model->d_group_table) == cudaSuccess) {
+            model->group_geo = group;
+        } else {
+            cudaFree(model->d_group_table);
+            model->d_group_table = nullptr;
+            (void)cudaGetLastError();
+        }
     }
     *out = model;
     return MSV_OK;
@@ -163,6 +202,7 @@ int msv_cuda_viterbi_model_destroy(msv_viterbi_model* model) {
     {
         Device_guard guard(model->device);
         cudaFree(model->d_table);
+        cudaFree(model->d_group_table);
     }
     delete model;
     return MSV_OK;
@@ -170,7 +210,7 @@ int msv_cuda_viterbi_model_destroy(msv_viterbi_model* model) {
 
 int msv_cuda_viterbi_model_geometry(const msv_viterbi_model* model, int* columns_per_lane, int* threads_per_cta, size_t* shared_bytes) {
     if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
-    if (columns_per_lane) *columns_per_lane = model->geo->K;
+    if (columns_per_lane) *columns_per_lane = model->geo->K; // of the one-warp-per-sequence plan
     if (threads_per_cta) *threads_per_cta = model->geo->threads;
     if (shared_bytes) *shared_bytes = model->geo->shared_bytes();
     return MSV_OK;
@@ -184,9 +224,17 @@ int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scor
     Device_guard guard(model->device);
     MSV_CUDA_TRY(guard.status);
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-    const Viterbi_geometry* geo = model->geo;
+    // Eight lanes per sequence when the model is short and every slot gets enough work to balance (it has four times more
+    // slots than the warp plan; same criterion as the MSV planner: rows per slot vs the longest sequence).
+    // MSV_CUDA_VITERBI_GROUPS=0 / 1 forces the choice (tuning and test aid).
+    const char* forced = std::getenv("MSV_CUDA_VITERBI_GROUPS");
+    const bool balanced = model->group_geo &&
+                          4 * (db->total / (static_cast<uint64_t>(model->sm_count) * (model->group_geo->threads / 8))) >=
+                              3 * std::max<uint64_t>(db->longest, 1);
+    const bool grouped = model->group_geo && (forced ? forced[0] == '1' : balanced);
+    const Viterbi_geometry* geo = grouped ? model->group_geo : model->geo;
     msv::Scan_params p{};
-    p.table = model->d_table;
+    p.table = grouped ? model->d_group_table : model->d_table;
     p.residues = db->d_residues;
     p.offsets = db->d_offsets;
     p.order = db->d_order;
@@ -201,10 +249,12 @@ int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scor
     p.tr_E_J = model->tr_E_J;
     p.n_mirrors = 0;
     MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, sizeof(unsigned int), stream));
-    // persistent CTAs, one per SM, one warp per sequence in flight; fewer warps when there are fewer sequences
+    // persistent CTAs, one per SM, one warp per sequence (or per four) in flight; fewer warps when there are fewer sequences
     const size_t warps_per_cta = static_cast<size_t>(geo->threads) / 32;
-    const size_t ctas = std::max<size_t>(1, std::min<size_t>(model->sm_count, (db->n + warps_per_cta - 1) / warps_per_cta));
-    const size_t warps = ctas == 1 ? std::min(warps_per_cta, db->n) : std::min(warps_per_cta, (db->n + ctas - 1) / ctas);
+    const size_t per_warp = 32 / static_cast<size_t>(geo->G);
+    const size_t warps_wanted = (db->n + per_warp - 1) / per_warp;
+    const size_t ctas = std::max<size_t>(1, std::min<size_t>(model->sm_count, (warps_wanted + warps_per_cta - 1) / warps_per_cta));
+    const size_t warps = ctas == 1 ? std::min(warps_per_cta, warps_wanted) : std::min(warps_per_cta, (warps_wanted + ctas - 1) / ctas);
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
     // speculative rows unless the database is one of long sequences, which would mostly be scanned twice
     const bool speculate = db->total / db->n <= msv::kViterbiSpeculationMaxLength / 2 && !std::getenv("MSV_CUDA_NO_SPECULATION");

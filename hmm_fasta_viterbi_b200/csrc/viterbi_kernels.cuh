@@ -269,4 +269,234 @@ __global__ void __launch_bounds__(THREADS, 1) viterbi_scan_warp_kernel(const Sca
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_slot), "n"(TMEM_COLUMNS) : "memory");
 }
 
+// =====================================================================================================================
+// Lane-group variant for SHORT models: G = 8 lanes per sequence, four sequences per warp.
+//
+// With one warp per sequence a 100- or 200-column model leaves each lane 4 or 8 columns: the per-row bookkeeping outweighs
+// the cells and a carried-in delete path often outlives a whole lane, so the hand-over repeats.  Here a lane keeps K = 16 ..
+// 56 columns of one of FOUR sequences; bookkeeping, votes and the tensor-memory transition loads (their addresses do not
+// depend on the residue, so they stay warp-uniform; every group reads the same values, replicated over the 32 TMEM lanes)
+// are shared by the four.  Emissions differ per group and come from shared memory, [residue][q][lane of group][4].
+// Groups retire and fetch sequences independently; rows run in warp-uniform chunks (the minimum over the groups of their
+// remaining rows), as in msv_scan_kernel.  Exact rows only (the group-wide E is three shuffles).
+// Table: as for the warp kernel with 32 replaced by G in the shared-memory part and in the edge block; the tensor-memory
+// part is [32 lanes][...] with lane l holding the transitions of group lane l % G.
+// =====================================================================================================================
+template <int G, int K, int THREADS, bool CJ_SAME>
+__global__ void __launch_bounds__(THREADS, 1) viterbi_scan_group_kernel(const Scan_params p) {
+    static_assert(G == 8 || G == 16, "lanes per sequence");
+    static_assert(K % 4 == 0 && K >= 4 && K <= kViterbiMaxColumnsPerLane, "columns per lane");
+    constexpr int Q = K / 4;
+    constexpr uint32_t QUAD_BYTES = G * 16;
+    constexpr uint32_t ROW_BYTES = K * G * 4;
+    constexpr uint32_t EMISSION_BYTES = kAlphabet * ROW_BYTES;
+    constexpr uint32_t SMEM_TABLE_BYTES = EMISSION_BYTES + 2 * ROW_BYTES;
+    constexpr uint32_t TENSOR_WORDS = 5 * K;
+    constexpr uint32_t COPY_CHUNK = 32768;
+    constexpr uint32_t TMEM_COLUMNS = 512;
+    static_assert(TENSOR_WORDS <= TMEM_COLUMNS, "transitions of one lane must fit its tensor-memory lane");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t table_ready;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int gl = lane & (G - 1);
+
+    if (p.first_bad != nullptr && *p.first_bad != ~0ull) return;
+
+    if (threadIdx.x == 0) mbarrier_init(&table_ready, 1);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "n"(TMEM_COLUMNS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (threadIdx.x == 0) {
+        mbarrier_expect_tx(&table_ready, SMEM_TABLE_BYTES);
+#pragma unroll 1
+        for (uint32_t at = 0; at < SMEM_TABLE_BYTES; at += COPY_CHUNK) {
+            const uint32_t bytes = min(COPY_CHUNK, SMEM_TABLE_BYTES - at);
+            tma_bulk_load(smem_raw + at, reinterpret_cast<const unsigned char*>(p.table) + at, bytes, &table_ready);
+        }
+    }
+    const float* tensor_src = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(p.table) + SMEM_TABLE_BYTES);
+    const uint32_t tmem_lane_base = tmem_base_slot + ((static_cast<uint32_t>(warp & 3) * 32u) << 16);
+    if (warp < 4) {
+        const float2* src = reinterpret_cast<const float2*>(tensor_src + static_cast<size_t>(lane) * TENSOR_WORDS);
+#pragma unroll 4
+        for (uint32_t w = 0; w < TENSOR_WORDS / 2; ++w) {
+            const float2 a = __ldg(src + w);
+            tmem_store2(tmem_lane_base + 2 * w, a.x, a.y);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mbarrier_wait(&table_ready, 0);
+
+    const float4 edge = __ldg(reinterpret_cast<const float4*>(tensor_src + 32 * TENSOR_WORDS) + 2 * gl);
+    const float edge_dd = __ldg(tensor_src + 32 * TENSOR_WORDS + 8 * gl + 4);
+    const uint32_t tab_lane = smem_u32(smem_raw) + gl * 16;
+    const uint32_t md_lane = tab_lane + EMISSION_BYTES, dd_lane = md_lane + ROW_BYTES;
+    const float4 dd_first = lds128(dd_lane);
+    const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
+    const int left_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1)); // rotate inside the group
+    const float NEG_INF = __int_as_float(0xff800000);
+    const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
+
+    float m[K], in[K], d[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) m[j] = in[j] = d[j] = NEG_INF;
+    float J = NEG_INF, C = NEG_INF, N = 0.0f, B = NEG_INF, loop = 0.0f, move = 0.0f;
+    uint32_t remaining = 0, idx = 0;
+    bool active = false, done = false;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues);
+    uint32_t wlo = 0, whi = 0, phase = 0; // residue window of the group's sequence: next residue = byte phase/8 of (whi:wlo)
+
+    float tq[2][20];
+    tmem_load<20>(tmem_lane_base, tq[0]);
+
+    auto row = [&](const uint32_t x) {
+        const uint32_t erow = tab_lane + x * ROW_BYTES;
+        const float bt = B + tBMk;
+        const float a_last = fmaxf(fmaxf(m[K - 1] + edge.x, in[K - 1] + edge.y), d[K - 1] + edge.z);
+        float a_prev = __shfl_sync(0xffffffffu, a_last, left_lane); // the group's last lane hands -inf to its first
+        float e = NEG_INF;
+        float md_prev = NEG_INF, dd_prev = NEG_INF;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            float* t = tq[q & 1];
+            tmem_wait<20>(t);
+            if (q + 1 < Q) tmem_load<20>(tmem_lane_base + (q + 1) * 20, tq[(q + 1) & 1]);
+            const float4 ev = lds128(erow + q * QUAD_BYTES);
+            const float4 md4 = lds128_volatile(md_lane + q * QUAD_BYTES), dd4 = lds128_volatile(dd_lane + q * QUAD_BYTES);
+            const float em[4] = {ev.x, ev.y, ev.z, ev.w}, md[4] = {md4.x, md4.y, md4.z, md4.w}, dd[4] = {dd4.x, dd4.y, dd4.z, dd4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = 4 * q + c;
+                const float a = j == K - 1 ? a_last : fmaxf(fmaxf(m[j] + t[c], in[j] + t[4 + c]), d[j] + t[8 + c]);
+                const float ins = fmaxf(m[j] + t[12 + c], in[j] + t[16 + c]);
+                const float m_new = em[c] + fmaxf(a_prev, bt);
+                d[j] = j == 0 ? NEG_INF : fmaxf(m[j > 0 ? j - 1 : 0] + md_prev, d[j > 0 ? j - 1 : 0] + dd_prev);
+                m[j] = m_new;
+                in[j] = ins;
+                e = fmaxf(e, m_new);
+                a_prev = a;
+                md_prev = md[c];
+                dd_prev = dd[c];
+            }
+            if (q == Q - 1) tmem_load<20>(tmem_lane_base, tq[0]);
+        }
+        for (;;) { // delete paths that arrive from the lane to the left (see the warp kernel)
+            const float last_before = d[K - 1];
+            const float c_out = fmaxf(m[K - 1] + edge.w, d[K - 1] + edge_dd);
+            float carried = __shfl_sync(0xffffffffu, c_out, left_lane);
+            d[0] = fmaxf(d[0], carried);
+            carried = carried + dd_first.x;
+            d[1] = fmaxf(d[1], carried);
+            carried = carried + dd_first.y;
+            d[2] = fmaxf(d[2], carried);
+            carried = carried + dd_first.z;
+            d[3] = fmaxf(d[3], carried);
+            carried = carried + dd_first.w;
+            bool crossed = true;
+#pragma unroll
+            for (int q = 1; q < Q; ++q) {
+                const int j = 4 * q;
+                if (!__any_sync(0xffffffffu, carried > d[j])) {
+                    crossed = false;
+                    break;
+                }
+                const float4 dd = lds128_volatile(dd_lane + q * QUAD_BYTES);
+                d[j] = fmaxf(d[j], carried);
+                carried = carried + dd.x;
+                d[j + 1] = fmaxf(d[j + 1], carried);
+                carried = carried + dd.y;
+                d[j + 2] = fmaxf(d[j + 2], carried);
+                carried = carried + dd.z;
+                d[j + 3] = fmaxf(d[j + 3], carried);
+                carried = carried + dd.w;
+            }
+            if (!crossed || !__any_sync(0xffffffffu, d[K - 1] > last_before)) break;
+        }
+        if (gl == G - 1) e = fmaxf(e, d[K - 1]); // D[LENG] -> E
+#pragma unroll
+        for (int s = G / 2; s > 0; s >>= 1) e = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, s));
+        J = fmaxf(J + loop, e + tEJ);
+        if constexpr (!CJ_SAME) C = fmaxf(C + loop, e + tEC);
+        N = N + loop;
+        B = fmaxf(N, J) + move;
+    };
+
+    for (;;) {
+        while (remaining == 0 && !done) { // retire / fetch, group-uniform
+            if (active) {
+                if (gl == 0) store_score(p, idx, (CJ_SAME ? J : C) + move);
+                active = false;
+            }
+            uint32_t ticket = 0;
+            if (gl == 0) ticket = atomicAdd(p.queue_head, 1u);
+            ticket = __shfl_sync(gmask, ticket, 0, G);
+#pragma unroll
+            for (int j = 0; j < K; ++j) m[j] = in[j] = d[j] = NEG_INF;
+            J = NEG_INF;
+            C = NEG_INF;
+            N = 0.0f;
+            if (ticket >= p.n) { // finished groups keep executing rows on a dead state: everything stays -inf, no vote fires
+                done = true;
+                B = NEG_INF;
+                loop = 0.0f;
+                move = NEG_INF;
+                wp = reinterpret_cast<const uint32_t*>(p.residues);
+                wlo = whi = phase = 0;
+                break;
+            }
+            idx = __ldg(p.order + ticket);
+            const uint64_t begin = __ldg(p.offsets + idx);
+            const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
+            const float2 tr = __ldg(p.length_tr + len);
+            loop = tr.x;
+            move = tr.y;
+            B = move;
+            const uint32_t mis = static_cast<uint32_t>(begin) & 3u;
+            wp = reinterpret_cast<const uint32_t*>(p.residues + (begin - mis));
+            wlo = __ldg(wp);
+            whi = __ldg(wp + 1);
+            wp += 2;
+            phase = 8u * mis;
+            remaining = len;
+            active = true;
+        }
+        const uint32_t mine = done ? 0xffffffffu : remaining;
+        const uint32_t steps = __reduce_min_sync(0xffffffffu, mine);
+        if (steps == 0xffffffffu) break;
+        if (!done) remaining -= steps;
+        const uint32_t advance = done ? 0u : 1u;
+#pragma unroll 1
+        for (uint32_t t = steps; t > 0; --t) {
+            const uint32_t x = __funnelshift_r(wlo, whi, phase) & 0xffu;
+            phase += 8u;
+            if (phase == 32u) {
+                phase = 0;
+                wlo = whi;
+                whi = __ldg(wp);
+                wp += advance;
+            }
+            row(x);
+        }
+    }
+    tmem_wait<20>(tq[0]);
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_slot), "n"(TMEM_COLUMNS) : "memory");
+}
+
 } // namespace msv

@@ -168,6 +168,32 @@ def test_edge_cases_and_errors(oracle):
     assert err.value.status == -5
 
 
+@pytest.mark.parametrize("name", ["100.hmm", "200.hmm", "300.hmm", "400.hmm"])
+def test_lane_group_kernel_for_short_models(oracle, name, monkeypatch):
+    """Eight lanes per sequence, four sequences per warp (viterbi_scan_group_kernel): forced on, it must give the oracle's
+    bits on ragged inputs (empty sequences, single residues, hits with deletions) -- and so must the warp kernel."""
+    h = oracle.load_hmm(hmm_path(name))
+    model, table, logtr, tr3 = viterbi_model(oracle, h["match_emissions"], h["transitions"])
+    leng = h["model_length"] - 1
+    consensus = np.argmax(h["match_emissions"][1:], axis=1).astype(np.uint8)
+    rng = np.random.default_rng(leng + 3)
+    seqs = [rng.integers(0, 20, size=int(k), dtype=np.uint8) for k in rng.integers(0, 300, size=1500)]
+    for _ in range(300):  # hits, most with a deletion inside
+        a = int(rng.integers(0, leng - 40))
+        b = int(rng.integers(a + 10, min(leng - 10, a + 50)))
+        c = int(rng.integers(b, min(leng - 5, b + 30)))
+        seqs.append(np.concatenate([consensus[a:b], consensus[c:min(leng, c + 40)]]))
+    seqs += [np.zeros(0, np.uint8), np.array([7], np.uint8)]
+    codes, offsets = pack(seqs)
+    want = oracle.viterbi_score_batch(table, logtr, tr3, codes, offsets, threads=CORES)
+    db = msv.Database(codes, offsets)
+    monkeypatch.setenv("MSV_CUDA_VITERBI_GROUPS", "1")
+    assert ubits(db.viterbi(model)).tolist() == ubits(want).tolist()
+    assert ubits(db.viterbi(model)).tolist() == ubits(want).tolist()
+    monkeypatch.setenv("MSV_CUDA_VITERBI_GROUPS", "0")
+    assert ubits(db.viterbi(model)).tolist() == ubits(want).tolist()
+
+
 def test_speculative_rows_equal_exact_rows(oracle, monkeypatch):
     """The kernel assumes J <= N (B = N + move) and verifies once per sequence; hits (consensus-derived sequences) must be
     rescanned exactly, random sequences not; both kernels must return the oracle's bits."""

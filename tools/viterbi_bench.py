@@ -66,6 +66,7 @@ def main() -> None:
         cells = leng * float(offsets[-1])
         print(json.dumps({"model": name, "geometry": model.geometry, "sequences": len(packed), "ms": round(ms, 3),
                           "gcups": round(cells / ms / 1e6, 1), "cells_per_clk_per_sm": round(cells / (ms * 1e-3) / 148 / 1.965e9, 2),
+                          "groups_env": os.environ.get("MSV_CUDA_VITERBI_GROUPS"),
                           "mismatches": int((got.view(np.uint32) != want.view(np.uint32)).sum()), "checked": len(sample),
                           "oracle_gcups": round(leng * float(so[-1]) / t_cpu / 1e9, 3), "oracle_threads": cores}), flush=True)
         model.close()
