@@ -291,3 +291,28 @@ def test_msv_scan_two_stage_pipeline(tmp_path):
     rows = [line.split("\t") for line in out.stdout.splitlines() if not line.startswith("#")]
     assert [r[1] for r in rows] == ["200"], out.stdout + out.stderr
     assert float(rows[0][5]) < 1e-6 and float(rows[0][8]) < 1e-6 and float(rows[0][6]) > 100.0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_models_both_scans(oracle, seed):
+    """Fuzz: random model lengths (every columns-per-lane step up to 1300 columns gets hit over the seeds), emission rows
+    with impossible residues (probability 0 -> -inf scores), sparse transitions (probability 0), ragged databases.  MSV and
+    Viterbi through every default plan against their oracles, bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    for leng in (int(rng.integers(1, 60)), int(rng.integers(60, 450)), int(rng.integers(450, 1300))):
+        match, tr = random_model(rng, leng, spread=0.4)
+        match[rng.random(match.shape) < 0.05] = 0.0   # impossible residues
+        match[0] = 0
+        tr[rng.random(tr.shape) < 0.03] = 0.0         # impossible transitions
+        n = 5000 if leng < 450 else 1200
+        seqs = [rng.integers(0, 20, size=int(k), dtype=np.uint8) for k in rng.integers(0, 260, size=n)]
+        codes, offsets = pack(seqs)
+        table, tr3 = oracle.prepare(match)
+        logtr = oracle.viterbi_prepare(tr)
+        db = msv.Database(codes, offsets)
+        vit = msv.ViterbiModel(_cabi.emission_table(match), _cabi.viterbi_transitions(tr), *_cabi.model_transitions(leng + 1))
+        want = oracle.viterbi_score_batch(table, logtr, tr3, codes, offsets, threads=CORES)
+        assert ubits(db.viterbi(vit)).tolist() == ubits(want).tolist(), ("viterbi", leng)
+        model = msv.Model(_cabi.emission_table(match), *_cabi.model_transitions(leng + 1))
+        want = oracle.score_batch(table, tr3, codes, offsets, threads=CORES)
+        assert ubits(db.score(model)).tolist() == ubits(want).tolist(), ("msv", leng)
