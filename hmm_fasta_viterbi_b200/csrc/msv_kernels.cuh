@@ -6,10 +6,11 @@
 // and of the host loop that launches them 13 times per residue (MSV_HMM.cpp:382-423) into ONE launch per database.
 //
 // Three kernel families share one design (B200-first, not a translation):
-//   msv_scan_warp_kernel   one warp per sequence; emissions from shared memory AND tensor memory   -- the hot kernel
-//   msv_scan_kernel        G = 8/16/32 lanes per sequence, 32/G sequences per warp                  -- short models
-//   msv_scan_quad_kernel   four warps per sequence; table distributed over shared + tensor memory   -- few/long sequences,
-//                                                                                                     models > 2815 columns
+//   msv_scan_warp_kernel        one warp per sequence; emissions from shared memory AND tensor memory   -- the hot kernel
+//   msv_scan_kernel             G = 8/16/32 lanes per sequence, 32/G sequences per warp                  -- short models
+//   msv_scan_group_spec_kernel  the same with speculative rows + a device-side redo list                 -- shortest models
+//   msv_scan_quad_kernel        four warps per sequence; table distributed over shared + tensor memory   -- few/long sequences,
+//                                                                                                          models > 2815 columns
 // Common to all:
 //   * the lanes that own a sequence keep its DP row in REGISTERS (m[K]: K consecutive model columns per lane); the row
 //     never touches memory;
@@ -23,6 +24,9 @@
 //     tensor-memory part by tcgen05.st, read back with tcgen05.ld; columns beyond the model are -inf;
 //   * CTAs are persistent (one per SM); slots pull sequences longest-first from a global atomic queue;
 //   * residues stream from HBM as aligned 32-bit words (4 residues), prefetched one word ahead.
+//   * speculative rows (warp and shortest-model kernels): B = max(N, J) + move is N + move while J <= N, so the row needs no
+//     cross-lane E; one vote per sequence verifies it, failures are scanned again with the exact row (argument at
+//     msv_scan_warp_kernel).
 // Exactness: every cell performs the same fp32 add on the same operands as the reference; max is exact and
 // order-independent for the non-NaN values that can occur (-inf and finite numbers only), so scores are
 // bit-identical to the reference for any order of the E reduction.
