@@ -31,6 +31,8 @@ DECLARED_SYMBOLS = (
     "msv_cuda_db_score_device", "msv_cuda_db_score_gather", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
     "msv_cuda_db_filter_device", "msv_cuda_db_score_filter", "msv_cuda_host_register", "msv_cuda_host_unregister",
     "msv_cuda_launch_count",
+    "msv_cuda_score_batch_gather", "msv_cuda_model_device",
+    "msv_cuda_multi_create", "msv_cuda_multi_destroy", "msv_cuda_multi_score_batch", "msv_cuda_multi_gathered",
     "msv_host_viterbi_transitions", "msv_cuda_viterbi_model_create", "msv_cuda_viterbi_model_destroy",
     "msv_cuda_viterbi_model_geometry", "msv_cuda_db_viterbi_device", "msv_cuda_db_viterbi", "msv_cuda_db_viterbi_filter", "msv_cuda_viterbi_batch",
 )
@@ -91,6 +93,12 @@ lib.msv_cuda_db_viterbi_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C
 lib.msv_cuda_db_viterbi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_db_viterbi_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_viterbi_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+lib.msv_cuda_score_batch_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int, C.c_size_t]
+lib.msv_cuda_model_device.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+lib.msv_cuda_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+lib.msv_cuda_multi_destroy.argtypes = [C.c_void_p]
+lib.msv_cuda_multi_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+lib.msv_cuda_multi_gathered.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
 lib.msv_cuda_launch_count.restype = C.c_uint64
 lib.msv_cuda_launch_count.argtypes = [C.c_int]
 for _name in DECLARED_SYMBOLS:
@@ -171,6 +179,35 @@ def _ptr(a) -> int:
     return int(a.data_ptr())  # torch tensor
 
 
+def _host_batch(residues, offsets, out):
+    """Normalise the host buffers of an end-to-end call: uint8 codes, uint64 offsets (n+1), float32 result -- all
+    C-contiguous.  numpy inputs of another dtype/stride are converted; torch tensors (pinned buffers) must already fit."""
+    def conform(a, np_dtype, what):
+        if isinstance(a, np.ndarray):
+            return np.ascontiguousarray(a, np_dtype)
+        if hasattr(a, "data_ptr"):  # torch tensor: check instead of converting (a copy would lose the pinning)
+            itemsize = np.dtype(np_dtype).itemsize
+            if a.element_size() != itemsize or not a.is_contiguous() or a.is_floating_point() != (np_dtype == np.float32):
+                raise TypeError(f"{what}: expected a contiguous {np.dtype(np_dtype).name} buffer, got {a.dtype} (contiguous={a.is_contiguous()})")
+            return a
+        return np.ascontiguousarray(a, np_dtype)
+    offsets = conform(offsets, np.uint64, "offsets")
+    n = len(offsets) - 1
+    if n < 0:
+        raise ValueError("offsets needs n + 1 entries")
+    residues = conform(residues, np.uint8, "residues")
+    if out is None:
+        out = np.empty(n, np.float32)
+    elif isinstance(out, np.ndarray):
+        if out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"] or out.size < n:
+            raise TypeError("out: expected a C-contiguous float32 array of at least n entries")
+    else:
+        conform(out, np.float32, "out")
+        if out.numel() < n:
+            raise TypeError("out: fewer than n entries")
+    return residues, offsets, n, out
+
+
 class Model:
     """Device-resident model (msv_model*)."""
 
@@ -199,11 +236,16 @@ class Model:
 
     def score_batch(self, residues, offsets, out=None) -> np.ndarray:
         """End-to-end call with host buffers (numpy arrays or pinned torch tensors)."""
-        n = len(offsets) - 1
-        if out is None:
-            out = np.empty(n, np.float32)
+        residues, offsets, n, out = _host_batch(residues, offsets, out)
         check(lib.msv_cuda_score_batch(self.handle, _ptr(residues), _ptr(offsets), n, _ptr(out)))
         return out
+
+    def score_batch_gather(self, residues, offsets, gathered, first_index: int) -> None:
+        """End-to-end call of a sharded run: host buffers of this rank's slice in, scores out through the fused gather
+        (``gathered``: this GPU's copy of the whole score array first, then the peers' copies; device pointers / CUDA tensors)."""
+        residues, offsets, n, _ = _host_batch(residues, offsets, None)
+        ptrs = (C.c_void_p * len(gathered))(*[_ptr(g) for g in gathered])
+        check(lib.msv_cuda_score_batch_gather(self.handle, _ptr(residues), _ptr(offsets), n, ptrs, len(gathered), first_index))
 
     def score_sequence(self, codes: np.ndarray) -> np.float32:
         codes = np.ascontiguousarray(codes, np.uint8)
@@ -214,6 +256,42 @@ class Model:
     def close(self) -> None:
         if getattr(self, "handle", None):
             lib.msv_cuda_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+GATHER_HOST, GATHER_PEER, GATHER_NCCL = 0, 1, 2
+
+
+class MultiGpu:
+    """Several GPUs of one box from ONE process (msv_multi*): one ``Model`` per GPU, the host database cut by cell count."""
+
+    def __init__(self, models) -> None:
+        self.models = list(models)  # keeps them alive
+        handles = (C.c_void_p * len(self.models))(*[m.handle for m in self.models])
+        h = C.c_void_p()
+        check(lib.msv_cuda_multi_create(handles, len(self.models), C.byref(h)))
+        self.handle = h
+
+    def score_batch(self, residues, offsets, out=None, gather: int = GATHER_HOST) -> np.ndarray:
+        residues, offsets, n, out = _host_batch(residues, offsets, out)
+        check(lib.msv_cuda_multi_score_batch(self.handle, _ptr(residues), _ptr(offsets), n, _ptr(out), gather))
+        return out
+
+    def gathered(self) -> tuple[int, int, int]:
+        """(device pointer, n, device) of the whole job's scores left on the first GPU by a PEER / NCCL call."""
+        p, n, d = C.c_void_p(), C.c_size_t(), C.c_int()
+        check(lib.msv_cuda_multi_gathered(self.handle, C.byref(p), C.byref(n), C.byref(d)))
+        return int(p.value or 0), int(n.value), int(d.value)
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            lib.msv_cuda_multi_destroy(self.handle)
             self.handle = None
 
     def __del__(self) -> None:
@@ -244,9 +322,7 @@ class ViterbiModel:
         return {"lanes_per_sequence": 32, "columns_per_lane": k.value, "threads_per_cta": t.value, "shared_bytes": s.value}
 
     def score_batch(self, residues, offsets, out=None) -> np.ndarray:
-        n = len(offsets) - 1
-        if out is None:
-            out = np.empty(n, np.float32)
+        residues, offsets, n, out = _host_batch(residues, offsets, out)
         check(lib.msv_cuda_viterbi_batch(self.handle, _ptr(residues), _ptr(offsets), n, _ptr(out)))
         return out
 

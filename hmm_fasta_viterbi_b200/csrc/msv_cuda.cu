@@ -566,8 +566,10 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
 
 // End-to-end batch with the upload hidden behind the scan: the database is cut into contiguous stages of sequences;
 // stage s+1 is copied to the device (copy stream) while stage s is validated, bucketed and scanned (compute stream).
+// Scores go to `scores_host` (when not NULL) and stay in `d_scores_out` (NULL: the workspace's own buffer); `mirrors` are the
+// peers' copies of a fused gather (launch_scan).  Synchronous: returns after the validation verdict has been read back.
 int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n,
-                          float* scores_host) {
+                          float* scores_host, float* d_scores_out = nullptr, float* const* mirrors = nullptr, int n_mirrors = 0) {
     uint64_t total = 0, longest = 0;
     if (int rc = db_check_offsets(residues, offsets, n, &total, &longest)) return rc;
     if (!db->copy_stream) {
@@ -585,6 +587,7 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
     db->longest = longest;
     db_keep_lengths(db, offsets, n);
     if (n == 0) return MSV_OK;
+    float* const d_out = d_scores_out ? d_scores_out : db->d_scores;
 
     // Stages grow geometrically: the first one is small so that the scan starts almost immediately, and every later
     // upload (tens of GB/s over PCIe/C2C) finishes long before the scan of the stage before it (a few GB/s of residues).
@@ -605,19 +608,34 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
         if (bounds[stages] < n || stages == 0) bounds[++stages] = n;
     }
 
-    MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy));
-    MSV_CUDA_TRY(cudaMemsetAsync(db->d_residues + total, 0, msv::kResiduePadBytes + 16, copy));
-    for (int s = 0; s < stages; ++s) {
-        const size_t first = bounds[s], last = bounds[s + 1];
-        const uint64_t begin = offsets[first], end = offsets[last];
-        if (end > begin) MSV_CUDA_TRY(cudaMemcpyAsync(db->d_residues + begin, residues + begin, end - begin, cudaMemcpyHostToDevice, copy));
-        MSV_CUDA_TRY(cudaEventRecord(db->stage_copied[s], copy));
-        MSV_CUDA_TRY(cudaStreamWaitEvent(compute, db->stage_copied[s], 0));
-        if (int rc = db_prepare_range(db, first, last - first, begin, end, longest, compute)) return rc;
-        if (int rc = launch_scan(model, db, first, last - first, end - begin, s, db->d_scores, compute)) return rc;
+    const auto enqueue = [&]() -> int {
+        MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy));
+        MSV_CUDA_TRY(cudaMemsetAsync(db->d_residues + total, 0, msv::kResiduePadBytes + 16, copy));
+        for (int s = 0; s < stages; ++s) {
+            const size_t first = bounds[s], last = bounds[s + 1];
+            const uint64_t begin = offsets[first], end = offsets[last];
+            if (end > begin)
+                MSV_CUDA_TRY(cudaMemcpyAsync(db->d_residues + begin, residues + begin, end - begin, cudaMemcpyHostToDevice, copy));
+            MSV_CUDA_TRY(cudaEventRecord(db->stage_copied[s], copy));
+            MSV_CUDA_TRY(cudaStreamWaitEvent(compute, db->stage_copied[s], 0));
+            if (int rc = db_prepare_range(db, first, last - first, begin, end, longest, compute)) return rc;
+            if (int rc = launch_scan(model, db, first, last - first, end - begin, s, d_out, compute, mirrors, n_mirrors)) return rc;
+        }
+        if (scores_host) MSV_CUDA_TRY(cudaMemcpyAsync(scores_host, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, compute));
+        return db_read_validation(db, residues, compute);
+    };
+    const int rc = enqueue();
+    if (rc != MSV_OK) {
+        // copies that still read the caller's buffers (and kernels that use the workspace) may be queued: drain both streams
+        // before handing the buffers back, and leave the workspace empty
+        const std::string message = g_last_error;
+        (void)cudaStreamSynchronize(copy);
+        (void)cudaStreamSynchronize(compute);
+        (void)cudaGetLastError();
+        db->n = 0;
+        g_last_error = message;
     }
-    MSV_CUDA_TRY(cudaMemcpyAsync(scores_host, db->d_scores, n * sizeof(float), cudaMemcpyDeviceToHost, compute));
-    return db_read_validation(db, residues, compute);
+    return rc;
 }
 
 } // namespace
@@ -926,6 +944,32 @@ int msv_cuda_score_batch(msv_model* model, const uint8_t* residues, const uint64
         model->workspace->device = model->device;
     }
     return score_batch_pipelined(model, model->workspace, residues, offsets, n, scores_host);
+}
+
+int msv_cuda_score_batch_gather(msv_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* const* gathered,
+                                int n_gathered, size_t first_index) {
+    if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
+    if (n && !offsets) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_gathered < 1 || n_gathered > msv::kMaxScoreMirrors + 1 || !gathered)
+        return fail(MSV_ERR_INVALID_ARGUMENT, "between 1 and %d gathered arrays are supported", msv::kMaxScoreMirrors + 1);
+    for (int r = 0; r < n_gathered; ++r)
+        if (n && !gathered[r]) return fail(MSV_ERR_INVALID_ARGUMENT, "gathered[%d] is NULL", r);
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    if (!model->workspace) {
+        model->workspace = new (std::nothrow) msv_db();
+        if (!model->workspace) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+        model->workspace->device = model->device;
+    }
+    float* shifted[msv::kMaxScoreMirrors + 1];
+    for (int r = 0; r < n_gathered; ++r) shifted[r] = gathered[r] + first_index;
+    return score_batch_pipelined(model, model->workspace, residues, offsets, n, nullptr, shifted[0], shifted + 1, n_gathered - 1);
+}
+
+int msv_cuda_model_device(const msv_model* model, int* device) {
+    if (!model || !device) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
+    *device = model->device;
+    return MSV_OK;
 }
 
 int msv_cuda_db_filter_device(msv_db* db, const float* scores_device, float mu, float lambda, float* bits_device,

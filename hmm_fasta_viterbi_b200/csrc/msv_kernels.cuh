@@ -511,7 +511,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
         wp += 3;
         uint32_t word = __funnelshift_r(w0, w1, shift);
-        if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + (word & 0xffu) * KT, te);
+        // (an empty sequence's "first residue" is a foreign byte: clamp, as for every prefetch index below)
+        if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + min(word & 0xffu, static_cast<uint32_t>(kAlphabet - 1)) * KT, te);
         // long sequences are likely enough to contain a hit that speculating on them would mostly mean scanning them twice
         const bool speculate = SPEC && len <= kSpeculationMaxLength;
         const uint32_t quads = (!SPEC || speculate) ? len >> 2 : 0u;
@@ -536,12 +537,15 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
             row(x0, x1);
             row(x1, x2);
             row(x2, x3);
-            row(x3, __byte_perm(ahead, 0, 0x4440));
+            // the row after the last one of a sequence is somebody else's byte (the next sequence's, or memory that a later
+            // upload stage has not filled or validated yet): it only feeds the tensor-memory PREFETCH, whose result is then
+            // dropped, but it must never become a TMEM address outside the table -- hence the clamp to a real residue code
+            row(x3, min(__byte_perm(ahead, 0, 0x4440), static_cast<uint32_t>(kAlphabet - 1)));
             word = ahead;
         }
 #pragma unroll 1
         for (uint32_t r = (!SPEC || speculate) ? len & 3u : 0u; r > 0; --r) {
-            row(word & 0xffu, (word >> 8) & 0xffu);
+            row(word & 0xffu, min((word >> 8) & 0xffu, static_cast<uint32_t>(kAlphabet - 1)));
             word >>= 8;
         }
         if constexpr (SPEC) {
@@ -556,7 +560,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
                 if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + x * KT, te);
 #pragma unroll 1
                 for (uint32_t i = 0; i < len; ++i) {
-                    const uint32_t x_next = __ldg(rp + i + 1); // the byte after the last residue is another sequence's or padding
+                    // the byte after the last residue is another sequence's or padding: prefetch index only, clamped (see above)
+                    const uint32_t x_next = min(static_cast<uint32_t>(__ldg(rp + i + 1)), static_cast<uint32_t>(kAlphabet - 1));
                     any_row(Exact_row{}, x, x_next);
                     x = x_next;
                 }

@@ -83,7 +83,7 @@ lib.msvh_viterbi_filter.restype = C.c_long
 lib.msvh_viterbi_filter.argtypes = [_vp, _vp, C.c_float, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msvh_msv_filter.restype = C.c_long
 lib.msvh_msv_filter.argtypes = [_vp, _vp, C.c_float, C.c_size_t, _vp, _vp, _vp, _vp]
-lib.msvh_msv_parallel_run_on_packed_devices.argtypes = [_vp, _vp, C.POINTER(C.c_int), C.c_int, _f32]
+lib.msvh_msv_parallel_run_on_packed_devices.argtypes = [_vp, _vp, C.POINTER(C.c_int), C.c_int, C.c_int, _f32]
 
 
 def _raise(status: int) -> None:
@@ -234,8 +234,9 @@ class MSV_HMM:
             _raise(status)
         return np.float32(out.value)
 
-    def parallel_run_on_sequences(self, database, devices=None) -> np.ndarray:
-        """Whole database in one call; `devices` (list of GPU indices) spreads it over several GPUs from this process."""
+    def parallel_run_on_sequences(self, database, devices=None, gather: str = "host") -> np.ndarray:
+        """Whole database in one call; `devices` (list of GPU indices) spreads it over several GPUs from this process,
+        `gather` = "host" | "peer" | "nccl" picks how the scores come together (MSV_HMM::Score_gather)."""
         if isinstance(database, FASTA_protein_sequences):
             database = Packed_sequences.from_fasta(database)
         out = np.empty(max(len(database), 1), np.float32)
@@ -246,7 +247,7 @@ class MSV_HMM:
             return out[: len(database)]
         if devices:
             arr = (C.c_int * len(devices))(*devices)
-            status = lib.msvh_msv_parallel_run_on_packed_devices(self._h, database._h, arr, len(devices), out)
+            status = lib.msvh_msv_parallel_run_on_packed_devices(self._h, database._h, arr, len(devices), {"host": 0, "peer": 1, "nccl": 2}[gather], out)
         else:
             status = lib.msvh_msv_parallel_run_on_packed(self._h, database._h, out)
         if status:

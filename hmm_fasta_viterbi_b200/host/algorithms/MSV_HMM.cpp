@@ -2,7 +2,6 @@
 
 #include <limits>
 #include <stdexcept>
-#include <thread>
 
 #include "msv_cuda.h"
 
@@ -29,6 +28,11 @@ Device_database::Device_database(const Packed_sequences& database, int device)
 // constructor (reference MSV_HMM.cpp:35-53).
 MSV_HMM::MSV_HMM(const Profile_HMM& base_hmm)
     : model_length(base_hmm.model_length), msv_mu(base_hmm.stats_local_msv_mu), msv_lambda(base_hmm.stats_local_msv_lambda) {
+    // a truncated .hmm leaves fewer nodes than LENG announces (the reader only prints a warning, like the reference's):
+    // never read past what was parsed
+    if (base_hmm.match_emissions.size() != model_length)
+        throw std::invalid_argument("MSV_HMM: profile HMM is incomplete (" + std::to_string(base_hmm.match_emissions.size()) +
+                                    " of " + std::to_string(model_length) + " nodes)");
     emission_scores.resize(NUM_OF_AMINO_ACIDS * model_length);
     if (model_length > 0) {
         msv_host_emission_table(base_hmm.match_emissions.front().data(), model_length, emission_scores.data());
@@ -129,36 +133,36 @@ std::vector<MSV_hit> MSV_HMM::msv_filter(const Device_database& database, float 
     return hits;
 }
 
-std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Packed_sequences& database, const std::vector<int>& devices) {
-    if (devices.empty()) throw std::invalid_argument("MSV_HMM::parallel_run_on_sequences: no devices given");
-    const auto parts = static_cast<int>(devices.size());
-    const auto bounds = database.cell_balanced_bounds(parts);
-    auto scores = std::vector<Log_score>(database.size());
-    auto failures = std::vector<std::string>(devices.size());
-    auto workers = std::vector<std::thread>();
-    for (int part = 0; part < parts; ++part) {
-        workers.emplace_back([&, part] {
-            try {
-                auto replica = MSV_HMM(*this); // own device model: the class is not re-entrant (reference MSV_HMM.cpp:59-64)
-                replica.set_device(devices[part]);
-                const auto first = bounds[part], last = bounds[part + 1];
-                if (first == last) return;
-                // offsets of the slice, rebased to its first residue
-                auto offsets = std::vector<uint64_t>(database.offsets.begin() + static_cast<std::ptrdiff_t>(first),
-                                                     database.offsets.begin() + static_cast<std::ptrdiff_t>(last) + 1);
-                const auto base = offsets.front();
-                for (auto& o : offsets) o -= base;
-                const auto status = msv_cuda_score_batch(replica.on_device(), database.residues.data() + base, offsets.data(),
-                                                         last - first, scores.data() + first);
-                if (status != MSV_OK) failures[part] = msv_cuda_last_error();
-            } catch (const std::exception& e) {
-                failures[part] = e.what();
-            }
-        });
+struct MSV_HMM::Replicas {
+    std::vector<int> devices;
+    std::vector<msv_model*> models;
+    msv_multi* multi = nullptr;
+    ~Replicas() {
+        msv_cuda_multi_destroy(multi);
+        for (auto* m : models) msv_cuda_model_destroy(m);
     }
-    for (auto& w : workers) w.join();
-    for (const auto& f : failures)
-        if (!f.empty()) throw std::runtime_error("MSV_HMM::parallel_run_on_sequences: " + f);
+};
+
+std::vector<Log_score> MSV_HMM::parallel_run_on_sequences(const Packed_sequences& database, const std::vector<int>& devices,
+                                                          Score_gather gather) {
+    if (devices.empty()) throw std::invalid_argument("MSV_HMM::parallel_run_on_sequences: no devices given");
+    if (!replicas || replicas->devices != devices) {
+        auto fresh = std::make_shared<Replicas>();
+        fresh->devices = devices;
+        for (const auto device : devices) {
+            msv_model* raw = nullptr;
+            const auto status = msv_cuda_model_create(emission_scores.data(), model_length, tr_B_Mk, tr_E_C, tr_E_J, device, &raw);
+            if (status != MSV_OK) throw_last_error("MSV_HMM: cannot create the device model", status);
+            fresh->models.push_back(raw);
+        }
+        const auto status = msv_cuda_multi_create(fresh->models.data(), static_cast<int>(fresh->models.size()), &fresh->multi);
+        if (status != MSV_OK) throw_last_error("MSV_HMM: cannot set up the multi-GPU scan", status);
+        replicas = fresh;
+    }
+    auto scores = std::vector<Log_score>(database.size());
+    const auto status = msv_cuda_multi_score_batch(replicas->multi, database.residues.data(), database.offsets.data(), database.size(),
+                                                   scores.data(), static_cast<int>(gather));
+    if (status != MSV_OK) throw_last_error("MSV_HMM::parallel_run_on_sequences", status);
     return scores;
 }
 

@@ -33,6 +33,7 @@ typedef std::string Kernels_source_code; // kernels are compiled in; nothing is 
 
 struct msv_model; // opaque device model of the C ABI
 struct msv_db;    // opaque device-resident database of the C ABI
+struct msv_multi; // opaque multi-GPU handle of the C ABI
 
 // A sequence database uploaded once and kept in HBM (validated, bucketed longest-first), to be scanned by any number of
 // models without touching the host again -- the natural shape of "all models against one database"
@@ -84,10 +85,14 @@ class MSV_HMM {
     // (Profile_HMM.hpp:34-35) but stops at the raw score.
     std::vector<MSV_hit> msv_filter(const Device_database& database, float threshold = 0.02f);
 
-    // The same over several GPUs of one box from ONE process: the database is cut into contiguous slices of equal
-    // cell count, one host thread and one device model per GPU; scores land directly in the result vector, so there
-    // is no collective.  (The one-process-per-GPU variant with an NCCL gather is hmm_fasta_viterbi_b200/sharded.py.)
-    std::vector<Log_score> parallel_run_on_sequences(const Packed_sequences& database, const std::vector<int>& devices);
+    // The same over several GPUs of one box from ONE process (msv_cuda_multi_score_batch): the database is cut into
+    // contiguous slices of equal cell count, one host thread and one device model per GPU.  `gather` says how the scores
+    // come together: every GPU downloads its slice straight into the result (host), the scan kernels store them into one
+    // array on the first GPU over NVLink peer access (peer), or one grouped NCCL send/receive round does (nccl).  Same bits.
+    // (The one-process-per-GPU variant is hmm_fasta_viterbi_b200/sharded.py + bench.py.)
+    enum class Score_gather { host = 0, peer = 1, nccl = 2 };
+    std::vector<Log_score> parallel_run_on_sequences(const Packed_sequences& database, const std::vector<int>& devices,
+                                                     Score_gather gather = Score_gather::host);
 
     size_t length() const { return model_length; } // LENG + 1
     int device() const { return device_index; }
@@ -104,6 +109,10 @@ class MSV_HMM {
 
     int device_index = 0;
     std::shared_ptr<msv_model> device_model; // created on first GPU call, shared by copies
+
+    // several GPUs from one process: one device model per GPU + the C ABI's multi-GPU handle, built on first use
+    struct Replicas;
+    std::shared_ptr<Replicas> replicas;
 
     msv_model* on_device();
 };

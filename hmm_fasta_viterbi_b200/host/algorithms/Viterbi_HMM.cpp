@@ -18,6 +18,8 @@ namespace {
 // Every logf of the model is evaluated here, on the host, by the helpers all bindings share.
 Viterbi_HMM::Viterbi_HMM(const Profile_HMM& base_hmm)
     : model_length(base_hmm.model_length), mu(base_hmm.stats_local_viterbi_mu), lambda(base_hmm.stats_local_viterbi_lambda) {
+    if (base_hmm.match_emissions.size() != model_length || base_hmm.transitions.size() != model_length)
+        throw std::invalid_argument("Viterbi_HMM: profile HMM is incomplete");
     emission_scores.resize(NUM_OF_AMINO_ACIDS * model_length);
     log_transitions.resize(NUM_OF_TRANSITIONS * model_length);
     if (model_length > 0) {

@@ -158,10 +158,11 @@ long msvh_msv_filter(void* m, void* d, float threshold, size_t capacity, uint64_
     return status == 0 ? found : status;
 }
 
-int msvh_msv_parallel_run_on_packed_devices(void* m, void* packed, const int* devices, int n_devices, float* scores) {
+int msvh_msv_parallel_run_on_packed_devices(void* m, void* packed, const int* devices, int n_devices, int gather, float* scores) {
     return guarded([&] {
         const auto got = static_cast<MSV_HMM*>(m)->parallel_run_on_sequences(*static_cast<Packed_sequences*>(packed),
-                                                                             std::vector<int>(devices, devices + n_devices));
+                                                                             std::vector<int>(devices, devices + n_devices),
+                                                                             static_cast<MSV_HMM::Score_gather>(gather));
         if (!got.empty()) std::memcpy(scores, got.data(), got.size() * sizeof(float));
     });
 }

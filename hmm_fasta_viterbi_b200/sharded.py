@@ -58,7 +58,10 @@ class FusedGather:
     raises otherwise -- callers fall back to ``gather_scores``.
     """
 
-    def __init__(self, slot: int, device, group=None) -> None:
+    def __init__(self, slot: int, device, group=None, total: int | None = None, first_index: int | None = None) -> None:
+        """Default layout: ``world`` slots of ``slot`` floats, rank r's shard at ``r * slot``.  With ``total`` and
+        ``first_index`` the buffer is the job's score array itself (``total`` floats, global sequence order) and this
+        rank's shard starts at ``first_index`` -- the layout of a cell-balanced cut of ONE database."""
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -67,14 +70,24 @@ class FusedGather:
         self.world, self.rank, self.slot = dist.get_world_size(group), dist.get_rank(group), max(int(slot), 1)
         if self.world > 8:
             raise ValueError("the fused gather addresses at most 8 GPUs (one NVSwitch domain)")
-        self.scores = symm_mem.empty(self.world * self.slot, dtype=torch.float32, device=device)
+        if total is None:
+            total, first_index = self.world * self.slot, self.rank * self.slot
+        self.total, self.first_index = max(int(total), 1), int(first_index or 0)
+        self.scores = symm_mem.empty(self.total, dtype=torch.float32, device=device)
         self.scores.fill_(float("nan"))
         self._handle = symm_mem.rendezvous(self.scores, group)
         ptrs = [int(p) for p in self._handle.buffer_ptrs]
         self._copies = [ptrs[self.rank]] + [ptrs[r] for r in range(self.world) if r != self.rank]  # own copy first
 
     def scan(self, model, database, stream: int = 0) -> None:
-        database.score_gather(model, self._copies, self.rank * self.slot, stream)
+        """Resident database: one launch + the device-side barrier, asynchronous on the current stream."""
+        database.score_gather(model, self._copies, self.first_index, stream)
+        self._handle.barrier(channel=0)
+
+    def scan_host(self, model, residues, offsets) -> None:
+        """End to end: this rank's HOST buffers in (msv_cuda_score_batch_gather: upload, bucketing and scan pipelined,
+        scores stored into every rank's copy), then the device-side barrier.  Synchronous for this rank's scan."""
+        model.score_batch_gather(residues, offsets, self._copies, self.first_index)
         self._handle.barrier(channel=0)
 
     def shard(self, r: int, count: int):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MSV_CUDA_ABI_VERSION 2
+#define MSV_CUDA_ABI_VERSION 3
 #define MSV_ALPHABET 20
 #define MSV_TRANSITIONS 7 /* m->m m->i m->d i->m i->i d->m d->d, the order of Profile_HMM::transitions (Profile_HMM.hpp:29) */
 
@@ -123,8 +123,38 @@ int msv_cuda_db_score(msv_model* model, msv_db* db, float* scores_host);
 /* end-to-end path with HOST buffers in and out: upload + bucket + scan + download in one synchronous call.
  * This is what MSV_HMM::parallel_run_on_sequences (the batch entry point the C++ class adds) calls. */
 int msv_cuda_score_batch(msv_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host);
+/* The end-to-end call of a SHARDED run (one process per GPU): HOST buffers of this rank's slice in, and the scores leave
+ * through the fused gather of msv_cuda_db_score_gather -- local sequence q goes to gathered[r][first_index + q] for every
+ * r < n_gathered (this GPU's copy first, then the peers' copies mapped over NVLink) -- instead of a host array.  Upload,
+ * validation, bucketing and scan are pipelined as in msv_cuda_score_batch.  Synchronous for THIS GPU's work; the caller
+ * then runs its cross-rank barrier (bench.py: the symmetric-memory barrier) before anybody reads the gathered array. */
+int msv_cuda_score_batch_gather(msv_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* const* gathered,
+                                int n_gathered, size_t first_index);
+/* the CUDA device a model lives on */
+int msv_cuda_model_device(const msv_model* model, int* device);
 /* one sequence, synchronous: the body of MSV_HMM::parallel_run_on_sequence (reference MSV_HMM.cpp:269-430). */
 int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Several GPUs of one box from ONE process.  The reference has no multi-device path (single context, queue on its first
+ * device: MSV_HMM.cpp:230,317).  The host database is cut into `ngpu` contiguous slices of equal DP-cell count
+ * (msv_host_partition_by_cells); slice g is uploaded to and scanned on models[g]'s GPU by its own host thread, pipelined
+ * like msv_cuda_score_batch.  The scan has no exchange step; `gather` selects how the fp32 scores come together:
+ *   MSV_GATHER_HOST  every GPU downloads its slice straight into scores_host (no device-side gather);
+ *   MSV_GATHER_PEER  the scan kernels store every score into ONE array on models[0]'s GPU over NVLink peer access (the
+ *                    fused gather of msv_cuda_db_score_gather), then one download;
+ *   MSV_GATHER_NCCL  every GPU scans into its own buffer, one grouped ncclSend / ncclRecv round (communicators from
+ *                    ncclCommInitAll; libnccl.so.2 is bound at run time) collects them on models[0]'s GPU, then one download.
+ * After a PEER or NCCL call the whole job's scores also stay resident on models[0]'s GPU (msv_cuda_multi_gathered) for
+ * device-side follow-up stages.  Scores are the same bits in every mode.  `models` (one per GPU, same model) are not owned.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct msv_multi msv_multi;
+enum { MSV_GATHER_HOST = 0, MSV_GATHER_PEER = 1, MSV_GATHER_NCCL = 2 };
+int msv_cuda_multi_create(msv_model* const* models, int ngpu, msv_multi** out);
+int msv_cuda_multi_destroy(msv_multi* multi);
+int msv_cuda_multi_score_batch(msv_multi* multi, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host,
+                               int gather);
+int msv_cuda_multi_gathered(const msv_multi* multi, const float** scores_device, size_t* n, int* device);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * MSV filter statistics (the step that follows the scan in HMMER3's pipeline; the reference parses the model's

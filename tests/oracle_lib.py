@@ -178,6 +178,35 @@ class Oracle:
         return out
 
 
+def synthetic_database(kind: str, count: int, seed: int, shortest: int = 10_000, longest: int = 35_000):
+    """BASELINE.json's synthetic workloads from oracle/synthetic_db.cpp (no product library involved):
+    kind 'swissprot_like' (configs 3/4) or 'long_uniform' (config 5).  Returns (codes uint8, offsets uint64[n+1])."""
+    if not os.path.exists(ORACLE_SO):
+        build_oracle()
+    L = C.CDLL(ORACLE_SO)
+    for fn in ("oracle_synthetic_swissprot_like", "oracle_synthetic_long_uniform"):
+        getattr(L, fn).restype = C.c_void_p
+    L.oracle_synthetic_swissprot_like.argtypes = [C.c_size_t, C.c_uint64]
+    L.oracle_synthetic_long_uniform.argtypes = [C.c_size_t, C.c_uint64, C.c_size_t, C.c_size_t]
+    L.oracle_synthetic_count.restype = C.c_size_t
+    L.oracle_synthetic_count.argtypes = [C.c_void_p]
+    L.oracle_synthetic_residues.restype = C.POINTER(C.c_uint8)
+    L.oracle_synthetic_residues.argtypes = [C.c_void_p]
+    L.oracle_synthetic_offsets.restype = C.POINTER(C.c_uint64)
+    L.oracle_synthetic_offsets.argtypes = [C.c_void_p]
+    L.oracle_synthetic_free.argtypes = [C.c_void_p]
+    h = (L.oracle_synthetic_swissprot_like(count, seed) if kind == "swissprot_like"
+         else L.oracle_synthetic_long_uniform(count, seed, shortest, longest))
+    try:
+        n = L.oracle_synthetic_count(h)
+        offsets = np.ctypeslib.as_array(L.oracle_synthetic_offsets(h), shape=(n + 1,)).copy()
+        total = int(offsets[-1])
+        codes = np.ctypeslib.as_array(L.oracle_synthetic_residues(h), shape=(max(total, 1),))[:total].copy()
+        return codes, offsets
+    finally:
+        L.oracle_synthetic_free(h)
+
+
 class RefLib:
     """The reference's own code (only where oracle/_ref/libmsv_ref.so exists)."""
 

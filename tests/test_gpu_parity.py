@@ -119,11 +119,19 @@ def test_every_kernel_geometry(oracle, geometry, monkeypatch):
     KT = parts[2] if len(parts) > 2 else -1
     limit = G * K - 1  # every kernel needs one padding column at the end of the row
     fits = [n for n in model_files() if int(n.split(".")[0]) <= limit]
-    if not fits:
-        pytest.skip("no fixture model fits this geometry")
-    name = fits[-1]
     monkeypatch.setenv("MSV_CUDA_GEOMETRY", geometry)
-    model, table, tr3 = device_model(oracle, name)
+    if fits:
+        name = fits[-1]
+        model, table, tr3 = device_model(oracle, name)
+    else:  # no fixture is this short (8 lanes x 4 columns): a synthetic model that fills the geometry
+        name = f"{limit}.synthetic"
+        rng = np.random.default_rng(limit)
+        match = np.zeros((limit + 1, 20), np.float32)
+        match[1:] = rng.dirichlet(np.full(20, 0.4), size=limit).astype(np.float32)
+        table, tr3 = oracle.prepare(match)
+        mine = _cabi.emission_table(match)
+        assert ubits(mine).tolist() == ubits(table).tolist()
+        model = msv.Model(mine, *_cabi.model_transitions(limit + 1))
     geo = model.geometry
     assert (geo["lanes_per_sequence"], geo["columns_per_lane"], geo["tensor_columns_per_lane"]) == (G, K, KT)
     rng = np.random.default_rng(G * 1000 + K)
@@ -365,8 +373,40 @@ def test_single_process_multi_device_driver(oracle):
     packed = msv.Packed_sequences.synthetic_swissprot_like(20_000, 9)
     one = model.parallel_run_on_sequences(packed)
     devices = [0, 1] if _cabi.device_count() > 1 else [0, 0]
-    two = model.parallel_run_on_sequences(packed, devices=devices + [0])
-    assert (ubits(one) == ubits(two)).all()
+    for gather in ("host", "peer", "nccl"):  # NCCL cannot put two ranks on one GPU: only where the box has several
+        if gather == "nccl" and _cabi.device_count() < 3:
+            continue
+        two = model.parallel_run_on_sequences(packed, devices=devices + [0 if _cabi.device_count() < 3 else 2], gather=gather)
+        assert (ubits(one) == ubits(two)).all(), gather
+
+
+def test_multi_gpu_c_abi(oracle):
+    """msv_cuda_multi_score_batch straight through the C ABI: the cell-balanced cut, one host thread per GPU, and the three
+    ways of bringing the scores together give the bits of a single-GPU call; the gathered array stays on the first GPU."""
+    import ctypes as C
+    devices = list(range(min(_cabi.device_count(), 4)))
+    if len(devices) == 1:
+        devices = [0, 0, 0]  # three slices, one GPU: still exercises the partitioner, the threads and the peer-store path
+    h = oracle.load_hmm(hmm_path("500.hmm"))
+    table = _cabi.emission_table(h["match_emissions"])
+    models = [msv.Model(table, *_cabi.model_transitions(h["model_length"]), device=d) for d in devices]
+    packed = msv.Packed_sequences.synthetic_swissprot_like(30_000, 12)
+    want = models[0].score_batch(packed.residues, packed.offsets)
+    multi = _cabi.MultiGpu(models)
+    modes = [_cabi.GATHER_HOST, _cabi.GATHER_PEER] + ([_cabi.GATHER_NCCL] if len(set(devices)) == len(devices) and len(devices) > 1 else [])
+    for mode in modes:
+        got = multi.score_batch(packed.residues, packed.offsets, gather=mode)
+        assert (ubits(got) == ubits(want)).all(), mode
+        if mode != _cabi.GATHER_HOST:
+            ptr, n, dev = multi.gathered()
+            assert n == len(packed) and dev == devices[0] and ptr
+            back = np.empty(n, np.float32)
+            C.CDLL("libcudart.so.12").cudaMemcpy(C.c_void_p(back.ctypes.data), C.c_void_p(ptr), C.c_size_t(4 * n), 2)
+            assert (ubits(back) == ubits(want)).all()
+    with pytest.raises(_cabi.MsvCudaError):
+        multi.score_batch(packed.residues, packed.offsets, gather=7)
+    assert multi.score_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64)).size == 0
+    multi.close()
 
 
 def test_filter_statistics_bits_and_pvalues(oracle):
@@ -426,6 +466,29 @@ def test_bad_residue_code_is_reported_not_scored(oracle):
         msv.MSV_HMM(msv.Profile_HMM(hmm_path("100.hmm"))).parallel_run_on_sequence("#ACDZ")
 
 
+def test_bad_residue_at_an_upload_stage_boundary(oracle):
+    """msv_cuda_score_batch scans stage s while stage s+1 is still uploading.  The last sequence of a stage prefetches the
+    tensor-memory row of "the residue after its last one" -- the first byte of the next stage, which may be unvalidated
+    (here: code 255).  It must come back as MSV_ERR_BAD_RESIDUE, not as a fault, and the workspace must be reusable."""
+    model, table, tr3 = device_model(oracle, "1400.hmm")
+    packed = msv.Packed_sequences.synthetic_swissprot_like(60_000, 5)
+    codes, offsets = packed.residues.copy(), packed.offsets.copy()
+    good = model.score_batch(codes, offsets)
+    # the first cut of the pipelined upload is the first sequence boundary at or after 2 MiB
+    q = int(np.searchsorted(offsets, 2 << 20))
+    for position in (int(offsets[q]), int(offsets[q]) + 1, int(offsets[-1]) - 1):
+        broken = codes.copy()
+        broken[position] = 255
+        with pytest.raises(_cabi.MsvCudaError) as err:
+            model.score_batch(broken, offsets)
+        assert err.value.status == _cabi.MSV_ERR_BAD_RESIDUE and f"position {position}" in str(err.value)
+        again = model.score_batch(codes, offsets)  # same workspace, right after the failed batch
+        assert (ubits(again) == ubits(good)).all()
+    sample = np.arange(q - 3, q + 3)
+    sc, so = pack([codes[int(offsets[i]):int(offsets[i + 1])] for i in sample])
+    assert ubits(good[sample]).tolist() == ubits(oracle.score_batch(table, tr3, sc, so, threads=CORES)).tolist()
+
+
 def test_long_sequence_and_misaligned_offsets(oracle):
     """One titin-like sequence (config 5 shape, shortened) plus neighbours that start at every byte alignment."""
     model, table, tr3 = device_model(oracle, "2405.hmm")
@@ -474,6 +537,22 @@ def test_full_size_properties_config4(oracle):
     sl = np.arange(200_000, 230_000)[::-1]
     rc, ro = pack([codes[int(offsets[q]):int(offsets[q + 1])] for q in sl])
     assert (ubits(model.score_batch(rc, ro)) == ubits(first[sl])).all()
+
+
+@pytest.mark.timeout(1500)
+def test_full_size_exhaustive_config4(oracle):
+    """Slow (about a minute and a half of host time on 16 threads): EVERY one of the 1 000 000 scores of the bench workload
+    (1400.hmm x the seed-20261018 database, through the end-to-end call) against the reference's own compiled
+    run_on_sequence (oracle/_ref), or the C restatement where that library is absent.  0 ULP."""
+    from oracle_lib import RefLib
+    model, table, tr3 = device_model(oracle, "1400.hmm")
+    packed = msv.Packed_sequences.synthetic_swissprot_like(1_000_000, 20261018)
+    got = model.score_batch(packed.residues, packed.offsets)
+    if RefLib.available():
+        want = RefLib().model(hmm_path("1400.hmm")).run_batch(packed.residues, packed.offsets, CORES)
+    else:
+        want = oracle.score_batch(table, tr3, packed.residues, packed.offsets, threads=CORES)
+    assert int((ubits(got) != ubits(want)).sum()) == 0
 
 
 def test_full_size_sample_parity_config3(oracle):
@@ -556,8 +635,16 @@ def test_fused_gather_two_gpus(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["n_gpus"] == 2 and "peer_gather_unavailable" not in line, line.get("peer_gather_unavailable")
-    assert line["config"]["gather"].startswith("fused into the scan kernel")
+    assert line["scaling"] == "strong" and line["warmup"] == 3
+    assert line["gather"].startswith("fused into the scan kernel")
     assert line["nccl_gather"]["same_bits_as_fused_gather_on_every_rank"] is True
+    # the end-to-end leg leaves the WHOLE job's scores in one host buffer on rank 0, checked against the CPU reference
+    assert line["parity"]["e2e_job_buffer_has_no_gaps"] and line["parity"]["e2e_job_buffer_equals_own_device_scan"]
+    checked = [v for k, v in line["parity"].items() if k.startswith("gathered_job_buffer_vs_")]
+    assert checked and checked[0]["mismatches"] == 0 and checked[0]["checked"] >= 1000
+    # ... and the single-process driver behind the C ABI (msv_cuda_multi_score_batch) gives the same bits in every gather mode
+    for mode in ("host", "peer", "nccl"):
+        assert line["single_process_multi_gpu"][mode].get("same_bits_as_multi_process_job_buffer") is True, line["single_process_multi_gpu"]
 
 
 # ---- speculative rows (B = N + move while J <= N) and their exact fallback ---------------------------------------------

@@ -13,7 +13,7 @@ import pytest
 import hmm_fasta_viterbi_b200 as msv
 from conftest import REPO, fasta_path, hmm_path, model_files
 from hmm_fasta_viterbi_b200 import _cabi
-from oracle_lib import LETTERS, pack
+from oracle_lib import LETTERS, pack, synthetic_database
 
 
 def bits(x) -> str:
@@ -35,7 +35,7 @@ def test_cabi_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _cabi.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if line.strip()}
     assert declared <= exported
-    assert _cabi.lib.msv_cuda_abi_version() == 2
+    assert _cabi.lib.msv_cuda_abi_version() == 3
 
 
 def test_cabi_has_no_torch_or_oracle_dependency():
@@ -205,3 +205,14 @@ def test_synthetic_databases_are_seeded_and_shaped():
     t = msv.Packed_sequences.synthetic_long_uniform(16, 2405, 10000, 35000)
     lens = np.diff(t.offsets.astype(np.int64))
     assert lens.min() >= 10000 and lens.max() <= 35000
+
+
+def test_checker_side_generator_builds_the_same_databases():
+    """bench.py's --impl reference arm builds its workload from oracle/synthetic_db.cpp so that it never loads the product
+    libraries; it must be the same database the product generator hands to the GPU arm."""
+    ours = msv.Packed_sequences.synthetic_swissprot_like(3000, 20261018)
+    codes, offsets = synthetic_database("swissprot_like", 3000, 20261018)
+    assert offsets.tolist() == ours.offsets.tolist() and (codes == ours.residues).all()
+    ours = msv.Packed_sequences.synthetic_long_uniform(8, 2405, 10000, 35000)
+    codes, offsets = synthetic_database("long_uniform", 8, 2405, 10000, 35000)
+    assert offsets.tolist() == ours.offsets.tolist() and (codes == ours.residues).all()
