@@ -691,8 +691,18 @@ def main() -> None:
             parity["e2e_job_buffer_has_no_gaps"] = bool(not np.isnan(job[:n_total]).any())
 
     # ---- single process, all GPUs, through the C ABI (msv_cuda_multi_score_batch); the other ranks wait ----
+    # (an NCCL barrier would leave a spinning kernel from another PROCESS on every other GPU, and two processes time-slice
+    # a GPU: the waiting ranks therefore wait on the host, through the rendezvous store)
+    def host_barrier(tag: str) -> None:
+        store = dist.distributed_c10d._get_default_store()
+        store.add(tag, 1)
+        while int(store.add(tag, 0)) < world:
+            time.sleep(0.002)
+
     single_process = None
     if world > 1 and not args.no_side_keys and strong:
+        torch.cuda.synchronize()
+        host_barrier("single_process_begin")
         if rank == 0:
             single_process = {}
             try:
@@ -722,7 +732,7 @@ def main() -> None:
             except Exception as e:  # noqa: BLE001
                 single_process = {"error": f"{type(e).__name__}: {e}"[:300]}
         torch.cuda.synchronize()
-        dist.barrier()
+        host_barrier("single_process_done")
 
     if rank == 0:
         value = cells_job * args.steps / (ms_total / 1e3) / 1e9

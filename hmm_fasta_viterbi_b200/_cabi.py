@@ -31,7 +31,8 @@ DECLARED_SYMBOLS = (
     "msv_cuda_db_score_device", "msv_cuda_db_score_gather", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
     "msv_cuda_db_filter_device", "msv_cuda_db_score_filter", "msv_cuda_host_register", "msv_cuda_host_unregister",
     "msv_cuda_launch_count",
-    "msv_cuda_score_batch_gather", "msv_cuda_model_device",
+    "msv_cuda_score_batch_gather", "msv_cuda_model_device", "msv_cuda_model_wave_geometry",
+    "msv_cuda_db_create_from_fasta", "msv_cuda_db_refill_from_fasta", "msv_cuda_db_download", "msv_cuda_score_fasta",
     "msv_cuda_multi_create", "msv_cuda_multi_destroy", "msv_cuda_multi_score_batch", "msv_cuda_multi_gathered",
     "msv_host_viterbi_transitions", "msv_cuda_viterbi_model_create", "msv_cuda_viterbi_model_destroy",
     "msv_cuda_viterbi_model_geometry", "msv_cuda_db_viterbi_device", "msv_cuda_db_viterbi", "msv_cuda_db_viterbi_filter", "msv_cuda_viterbi_batch",
@@ -95,6 +96,11 @@ lib.msv_cuda_db_viterbi_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.
 lib.msv_cuda_viterbi_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.msv_cuda_score_batch_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int, C.c_size_t]
 lib.msv_cuda_model_device.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+lib.msv_cuda_db_create_from_fasta.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+lib.msv_cuda_db_refill_from_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+lib.msv_cuda_db_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+lib.msv_cuda_score_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+lib.msv_cuda_model_wave_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
 lib.msv_cuda_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
 lib.msv_cuda_multi_destroy.argtypes = [C.c_void_p]
 lib.msv_cuda_multi_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
@@ -228,6 +234,13 @@ class Model:
         return {"lanes_per_sequence": g.value, "columns_per_lane": k.value, "tensor_columns_per_lane": kt.value,
                 "threads_per_cta": t.value, "shared_bytes": s.value}
 
+    @property
+    def wave_geometry(self) -> dict:
+        """Single-sequence latency kernel: columns per lane (0 = none), warps in the chain, CTAs in the cluster."""
+        k, w, c = C.c_int(), C.c_int(), C.c_int()
+        check(lib.msv_cuda_model_wave_geometry(self.handle, C.byref(k), C.byref(w), C.byref(c)))
+        return {"columns_per_lane": k.value, "warps": w.value, "ctas": c.value}
+
     def plan(self, database: "Database") -> dict:
         """Launch plan a scan of `database` would use: kernel family (lanes per sequence) and sequences per CTA."""
         lanes, per_cta = C.c_int(), C.c_int()
@@ -247,6 +260,21 @@ class Model:
         ptrs = (C.c_void_p * len(gathered))(*[_ptr(g) for g in gathered])
         check(lib.msv_cuda_score_batch_gather(self.handle, _ptr(residues), _ptr(offsets), n, ptrs, len(gathered), first_index))
 
+    def score_fasta(self, text) -> tuple[np.ndarray, int]:
+        """FASTA text (bytes, or a uint8 numpy array / np.memmap of a file) -> (scores, rejected records).  The raw text is
+        uploaded and parsed on the GPU (msv_cuda_db_refill_from_fasta into a database handle this model keeps), then scanned."""
+        buf = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else text
+        if not hasattr(self, "_fasta_db") or self._fasta_db is None:
+            self._fasta_db = Database(np.zeros(0, np.uint8), np.zeros(1, np.uint64), device=self.device)
+        rejected = self._fasta_db.refill_from_fasta(buf)
+        return self._fasta_db.score(self), rejected
+
+    def score_fasta_file(self, path: str) -> tuple[np.ndarray, int]:
+        """The same for a file: mapped, not read -- the pages go from the page cache straight into the pinned staging ring."""
+        if os.path.getsize(path) == 0:
+            return np.zeros(0, np.float32), 0
+        return self.score_fasta(np.memmap(path, dtype=np.uint8, mode="r"))
+
     def score_sequence(self, codes: np.ndarray) -> np.float32:
         codes = np.ascontiguousarray(codes, np.uint8)
         out = C.c_float()
@@ -254,6 +282,9 @@ class Model:
         return np.float32(out.value)
 
     def close(self) -> None:
+        if getattr(self, "_fasta_db", None) is not None:
+            self._fasta_db.close()
+            self._fasta_db = None
         if getattr(self, "handle", None):
             lib.msv_cuda_model_destroy(self.handle)
             self.handle = None
@@ -351,6 +382,28 @@ class Database:
         check(lib.msv_cuda_db_create(device, _ptr(residues), _ptr(offsets), self.n, C.byref(h)))
         self.handle = h
         self.device = device
+
+    @classmethod
+    def from_fasta(cls, text, device: int = 0) -> "Database":
+        """FASTA text (bytes / uint8 array / np.memmap) parsed on the GPU; `.rejected` = records dropped for a foreign character."""
+        self = cls(np.zeros(0, np.uint8), np.zeros(1, np.uint64), device=device)
+        self.rejected = self.refill_from_fasta(text)
+        return self
+
+    def refill_from_fasta(self, text) -> int:
+        buf = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else text
+        rejected = C.c_size_t(0)
+        check(lib.msv_cuda_db_refill_from_fasta(self.handle, buf.ctypes.data if buf.size else 0, buf.size, C.byref(rejected)))
+        self.n = self.info()["n"]
+        return int(rejected.value)
+
+    def download(self) -> tuple[np.ndarray, np.ndarray]:
+        """(residues uint8, offsets uint64[n+1]) as they sit on the device."""
+        meta = self.info()
+        residues = np.empty(max(meta["total_residues"], 1), np.uint8)
+        offsets = np.empty(meta["n"] + 1, np.uint64)
+        check(lib.msv_cuda_db_download(self.handle, residues.ctypes.data, offsets.ctypes.data))
+        return residues[: meta["total_residues"]], offsets
 
     def info(self) -> dict:
         n, total, longest = C.c_size_t(), C.c_uint64(), C.c_uint64()

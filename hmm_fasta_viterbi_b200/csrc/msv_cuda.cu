@@ -7,6 +7,7 @@
 #include "msv_cuda.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -19,6 +20,7 @@
 
 #include "msv_internal.hpp"
 #include "msv_kernels.cuh"
+#include "msv_wave_kernels.cuh"
 
 static thread_local std::string g_last_error;
 static thread_local uint64_t g_launches = 0;
@@ -204,6 +206,32 @@ const Geometry* choose_quad_geometry(size_t columns) {
     return nullptr;
 }
 
+// ---- single-sequence latency kernels (msv_wave_kernels.cuh), one pair per columns-per-lane K --------------------------
+constexpr size_t kWaveDefaultMaxWarps = 16; // default chain length limit (the smallest K that stays within it is chosen)
+struct Wave_kernels {
+    int K;
+    void (*with_inline_residues)(const msv::Wave_params, const msv::Wave_inline_residues);
+    void (*with_device_residues)(const msv::Wave_params, const msv::Wave_no_residues);
+};
+template <int K> constexpr Wave_kernels wave_entry() { return {K, msv::msv_wave_kernel<K, true>, msv::msv_wave_kernel<K, false>}; }
+const Wave_kernels g_wave_kernels[] = {wave_entry<2>(), wave_entry<4>(), wave_entry<6>(), wave_entry<8>(), wave_entry<12>(), wave_entry<16>()};
+
+// Columns per lane of the chain: more warps shorten a row (each warp has fewer cells) until per-row bookkeeping and the
+// pipeline fill dominate.  MSV_CUDA_WAVE_K overrides (tuning aid).
+const Wave_kernels* choose_wave_kernels(size_t columns) {
+    const size_t max_warps = static_cast<size_t>(msv::kWaveWarpsPerCta) * msv::kWaveMaxCtas;
+    int want = 0;
+    if (const char* env = std::getenv("MSV_CUDA_WAVE_K")) want = std::atoi(env);
+    const Wave_kernels* fallback = nullptr;
+    for (const auto& k : g_wave_kernels) {
+        const size_t warps = (columns + 32 * k.K - 1) / (32 * static_cast<size_t>(k.K));
+        if (warps > max_warps) continue;
+        if (k.K == want) return &k;
+        if (!fallback && (warps <= kWaveDefaultMaxWarps || k.K == 16)) fallback = &k;
+    }
+    return want ? nullptr : fallback;
+}
+
 } // namespace
 
 // ---- opaque handles ---------------------------------------------------------------------------------------------
@@ -224,6 +252,23 @@ struct msv_model {
     float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
     int sm_count = 0;
     msv_db* workspace = nullptr; // reused by msv_cuda_score_batch / msv_cuda_score_sequence
+    // single-sequence latency path (msv_wave_kernels.cuh): a chain of warps over a thread-block cluster; built when
+    // tr_E_C == tr_E_J (the kernel speculates B = N + move) and the chain fits a cluster
+    struct Wave {
+        int K = 0;               // columns per lane
+        uint32_t warps = 0, ctas = 0;
+        size_t shared_bytes = 0, shared_limit = 0;
+        float* d_table = nullptr;
+        msv::Wave_accumulator* d_accumulator = nullptr;
+        msv::Wave_result* h_result = nullptr; // pinned + mapped: the kernel writes the result, the host polls it
+        msv::Wave_result* d_result = nullptr; // the same memory as the device sees it
+        uint8_t* d_residues = nullptr;        // sequences too long for the kernel parameters
+        uint8_t* h_staging = nullptr;         // pinned
+        size_t capacity = 0;
+        cudaStream_t stream = nullptr;
+        uint32_t tag = 0;
+        const Wave_kernels* kernels = nullptr;
+    } wave;
 };
 
 namespace {
@@ -410,6 +455,8 @@ int db_fill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t
 namespace msv_detail {
 int db_refill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n) { return db_fill(db, residues, offsets, n, nullptr); }
 int db_free(msv_db* db) { return db_release(db); }
+int db_reserve_for(msv_db* db, uint64_t total, size_t n, uint64_t longest, cudaStream_t stream) { return db_reserve(db, total, n, longest, stream); }
+int db_bucket(msv_db* db, cudaStream_t stream) { return db_prepare_range(db, 0, db->n, 0, 0, db->longest, stream); }
 } // namespace msv_detail
 
 namespace {
@@ -640,6 +687,154 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
 
 } // namespace
 
+// ---- single-sequence latency path -----------------------------------------------------------------------------------
+namespace {
+
+void wave_release(msv_model* model) {
+    auto& w = model->wave;
+    cudaFree(w.d_table);
+    cudaFree(w.d_accumulator);
+    cudaFree(w.d_residues);
+    if (w.h_result) cudaFreeHost(w.h_result);
+    if (w.h_staging) cudaFreeHost(w.h_staging);
+    if (w.stream) cudaStreamDestroy(w.stream);
+    w = msv_model::Wave();
+}
+
+cudaError_t wave_build(msv_model* model, const float* emission_scores, size_t columns) {
+    auto& w = model->wave;
+    const Wave_kernels* kernels = choose_wave_kernels(columns);
+    if (!kernels || columns == 0) return cudaErrorInvalidConfiguration;
+    const int K = kernels->K;
+    const size_t warps = (columns + 32 * static_cast<size_t>(K) - 1) / (32 * static_cast<size_t>(K));
+    size_t ctas = 1;
+    while (ctas * msv::kWaveWarpsPerCta < warps) ctas *= 2; // cluster sizes 1, 2, 4, 8
+    // table: [warp][residue][pair][lane][2]; lane l of warp g owns model columns (g*32 + l)*K + 1 ... + K, -inf beyond the model
+    const size_t floats = ctas * msv::kWaveWarpsPerCta * MSV_ALPHABET * static_cast<size_t>(K) * 32;
+    std::vector<float> laid(floats, -std::numeric_limits<float>::infinity());
+    const size_t model_length = columns + 1;
+    for (size_t g = 0; g < warps; ++g)
+        for (int res = 0; res < MSV_ALPHABET; ++res)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int j = 0; j < K; ++j) {
+                    const size_t col = (g * 32 + lane) * K + j + 1;
+                    if (col > columns) continue;
+                    laid[(((g * MSV_ALPHABET + res) * (K / 2) + j / 2) * 32 + lane) * 2 + j % 2] = emission_scores[res * model_length + col];
+                }
+    w.K = K;
+    w.warps = static_cast<uint32_t>(warps);
+    w.ctas = static_cast<uint32_t>(ctas);
+    w.shared_bytes = static_cast<size_t>(msv::kWaveWarpsPerCta) * MSV_ALPHABET * K * 128; // the table slice; + 4 bytes per row of the sequence
+    int optin = 0;
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, model->device) != cudaSuccess || optin < 65536) return cudaErrorInvalidConfiguration;
+    w.shared_limit = static_cast<size_t>(optin) - 4096; // static shared memory of the kernel (mailboxes) + slack
+    if (w.shared_limit < w.shared_bytes + 4096) return cudaErrorInvalidConfiguration;
+    w.kernels = kernels;
+    cudaError_t err = cudaMalloc(&w.d_table, floats * sizeof(float));
+    if (err == cudaSuccess) err = cudaMemcpy(w.d_table, laid.data(), floats * sizeof(float), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMalloc(&w.d_accumulator, sizeof(msv::Wave_accumulator));
+    if (err == cudaSuccess) err = cudaMemset(w.d_accumulator, 0, sizeof(msv::Wave_accumulator));
+    if (err == cudaSuccess) err = cudaHostAlloc(&w.h_result, sizeof(msv::Wave_result), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (err == cudaSuccess) {
+        std::memset(w.h_result, 0, sizeof(msv::Wave_result));
+        err = cudaHostGetDevicePointer(&w.d_result, w.h_result, 0);
+    }
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels->with_inline_residues), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(w.shared_limit));
+    if (err == cudaSuccess)
+        err = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels->with_device_residues), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(w.shared_limit));
+    return err;
+}
+
+// Scores one sequence with the wavefront kernel.  *rescore is set when the kernel's speculation did not hold (the sequence
+// contains a real hit): the caller then runs the exact kernel.
+int wave_score(msv_model* model, const uint8_t* residues, size_t length, float* score, bool* rescore) {
+    auto& w = model->wave;
+    *rescore = false;
+    // every CTA keeps one word per row of the sequence next to its table slice; a sequence too long for that (tens of
+    // thousands of residues) goes to the four-warp kernel
+    const size_t shared_bytes = w.shared_bytes + (length + 3) / 4 * 16 + 16;
+    if (shared_bytes > w.shared_limit) {
+        *rescore = true;
+        return MSV_OK;
+    }
+    msv::Wave_params p{};
+    p.table = w.d_table;
+    p.accumulator = w.d_accumulator;
+    p.result = w.d_result;
+    p.length = static_cast<uint32_t>(length);
+    p.warps = w.warps;
+    p.tag = ++w.tag ? w.tag : ++w.tag; // never 0: that is what an untouched result slot holds
+    p.tr_B_Mk = model->tr_B_Mk;
+    p.tr_E_J = model->tr_E_J;
+    msv_host_length_transitions(length, &p.loop, &p.move); // host libm, reference MSV_HMM.cpp:59-64
+
+    cudaLaunchConfig_t config{};
+    config.gridDim = dim3(w.ctas);
+    config.blockDim = dim3(msv::kWaveWarpsPerCta * 32);
+    config.dynamicSmemBytes = shared_bytes;
+    config.stream = w.stream;
+    cudaLaunchAttribute cluster{};
+    cluster.id = cudaLaunchAttributeClusterDimension;
+    cluster.val.clusterDim.x = w.ctas;
+    cluster.val.clusterDim.y = 1;
+    cluster.val.clusterDim.z = 1;
+    config.attrs = &cluster;
+    config.numAttrs = 1;
+
+    if (length <= msv::kWaveInlineBytes) {
+        msv::Wave_inline_residues block; // the sequence rides in the kernel parameters: one launch, no copy
+        block.words[(length ? length - 1 : 0) / 4] = 0;
+        if (length) std::memcpy(block.words, residues, length);
+        MSV_CUDA_TRY(cudaLaunchKernelEx(&config, w.kernels->with_inline_residues, p, block));
+    } else {
+        const size_t padded = (length + 3) / 4 * 4;
+        if (padded > w.capacity) {
+            cudaFree(w.d_residues);
+            if (w.h_staging) cudaFreeHost(w.h_staging);
+            w.d_residues = nullptr;
+            w.h_staging = nullptr;
+            w.capacity = 0;
+            const size_t want = padded + padded / 4;
+            MSV_CUDA_TRY(cudaMalloc(&w.d_residues, want));
+            MSV_CUDA_TRY(cudaHostAlloc(&w.h_staging, want, cudaHostAllocPortable));
+            w.capacity = want;
+        }
+        std::memcpy(w.h_staging, residues, length);
+        std::memset(w.h_staging + length, 0, padded - length);
+        MSV_CUDA_TRY(cudaMemcpyAsync(w.d_residues, w.h_staging, padded, cudaMemcpyHostToDevice, w.stream));
+        p.residues = w.d_residues;
+        MSV_CUDA_TRY(cudaLaunchKernelEx(&config, w.kernels->with_device_residues, p, msv::Wave_no_residues{}));
+    }
+    ++g_launches;
+    // the kernel writes the result into pinned host memory; poll it (a stream query every so often notices a failed launch)
+    volatile msv::Wave_result* result = w.h_result;
+    for (uint32_t spins = 1; result->tag != p.tag; ++spins) {
+        if ((spins & 0x3ffu) == 0) {
+            const cudaError_t state = cudaStreamQuery(w.stream);
+            if (state != cudaErrorNotReady) {
+                MSV_CUDA_TRY(state);
+                if (result->tag != p.tag) return fail(MSV_ERR_CUDA, "the single-sequence kernel finished without a result");
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const uint32_t status = result->status;
+    if (status & 2u) {
+        size_t at = 0;
+        while (at < length && residues[at] < MSV_ALPHABET) ++at;
+        return fail(MSV_ERR_BAD_RESIDUE, "residue code %u at position %zu is outside 0..19", at < length ? static_cast<unsigned>(residues[at]) : 255u, at);
+    }
+    if (status & 1u) *rescore = true;
+    else *score = result->score;
+    return MSV_OK;
+}
+
+} // namespace
+
 // =====================================================================================================================
 extern "C" {
 
@@ -828,6 +1023,13 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
             return fail(MSV_ERR_MODEL_TOO_LONG, "emission table of a %zu-column model exceeds shared + tensor memory", columns);
         return fail(MSV_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(err));
     }
+    // the single-sequence latency plan is optional: any failure here just leaves the four-warp kernel in charge
+    if (std::memcmp(&tr_E_C, &tr_E_J, sizeof(float)) == 0 && !forced && !std::getenv("MSV_CUDA_NO_WAVE")) {
+        if (wave_build(model, emission_scores, columns) != cudaSuccess) {
+            wave_release(model);
+            (void)cudaGetLastError();
+        }
+    }
     *out = model;
     return MSV_OK;
 }
@@ -837,6 +1039,7 @@ int msv_cuda_model_destroy(msv_model* model) {
     db_release(model->workspace);
     {
         Device_guard guard(model->device);
+        wave_release(model);
         cudaFree(model->bulk.d_table);
         cudaFree(model->octet.d_table);
         cudaFree(model->quad.d_table);
@@ -854,6 +1057,14 @@ int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int
     if (tensor_columns_per_lane) *tensor_columns_per_lane = plan.geo->KT;
     if (threads_per_cta) *threads_per_cta = plan.geo->threads;
     if (shared_bytes) *shared_bytes = plan.shared_bytes;
+    return MSV_OK;
+}
+
+int msv_cuda_model_wave_geometry(const msv_model* model, int* columns_per_lane, int* warps, int* ctas) {
+    if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
+    if (columns_per_lane) *columns_per_lane = model->wave.kernels ? model->wave.K : 0;
+    if (warps) *warps = static_cast<int>(model->wave.warps);
+    if (ctas) *ctas = static_cast<int>(model->wave.ctas);
     return MSV_OK;
 }
 
@@ -966,6 +1177,31 @@ int msv_cuda_score_batch_gather(msv_model* model, const uint8_t* residues, const
     return score_batch_pipelined(model, model->workspace, residues, offsets, n, nullptr, shifted[0], shifted + 1, n_gathered - 1);
 }
 
+int msv_cuda_score_fasta(msv_model* model, const char* text, size_t bytes, float* scores_host, size_t capacity, size_t* n_sequences,
+                         size_t* rejected) {
+    if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
+    if (n_sequences) *n_sequences = 0;
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    if (!model->workspace) {
+        model->workspace = new (std::nothrow) msv_db();
+        if (!model->workspace) return fail(MSV_ERR_OUT_OF_MEMORY, "host allocation failed");
+        model->workspace->device = model->device;
+    }
+    msv_db* db = model->workspace;
+    if (int rc = msv_detail::db_fill_from_fasta(db, text, bytes, rejected)) {
+        db->n = 0;
+        return rc;
+    }
+    if (n_sequences) *n_sequences = db->n;
+    if (db->n > capacity) return fail(MSV_ERR_INVALID_ARGUMENT, "the text holds %zu sequences but scores_host has room for %zu", db->n, capacity);
+    if (db->n == 0) return MSV_OK;
+    if (!scores_host) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_host is NULL");
+    if (int rc = launch_scan(model, db, 0, db->n, db->total, 0, db->d_scores, nullptr)) return rc;
+    MSV_CUDA_TRY(cudaMemcpy(scores_host, db->d_scores, db->n * sizeof(float), cudaMemcpyDeviceToHost));
+    return MSV_OK;
+}
+
 int msv_cuda_model_device(const msv_model* model, int* device) {
     if (!model || !device) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL argument");
     *device = model->device;
@@ -1029,6 +1265,16 @@ int msv_cuda_host_unregister(const void* buffer) {
 
 int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score) {
     if (!score) return fail(MSV_ERR_INVALID_ARGUMENT, "score is NULL");
+    if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
+    if (length && !residues) return fail(MSV_ERR_INVALID_ARGUMENT, "residues is NULL");
+    if (model->wave.kernels && length < (1ull << 27)) {
+        Device_guard guard(model->device);
+        MSV_CUDA_TRY(guard.status);
+        bool rescore = false;
+        if (int rc = wave_score(model, residues, length, score, &rescore)) return rc;
+        if (!rescore) return MSV_OK;
+        // a real hit: J overtook N somewhere, the speculative rows do not apply -- the exact kernel below scores it
+    }
     const uint64_t offsets[2] = {0, length};
     return msv_cuda_score_batch(model, residues, offsets, 1, score);
 }

@@ -72,4 +72,11 @@ namespace msv_detail {
 // grow, so a workspace handle can be refilled call after call without reallocating (msv_cuda.cu)
 int db_refill(msv_db* db, const uint8_t* residues, const uint64_t* offsets, size_t n);
 int db_free(msv_db* db);
+// for producers that fill a database ON the device (fasta_cuda.cu): make room for `total` residues / `n` sequences and the
+// per-length transition table up to `longest` (queued on `stream`); then, once d_residues / d_offsets hold valid codes and
+// offsets and db->n / total / longest are set, bucket the sequences longest-first
+int db_reserve_for(msv_db* db, uint64_t total, size_t n, uint64_t longest, cudaStream_t stream);
+int db_bucket(msv_db* db, cudaStream_t stream);
+// FASTA text (host memory) -> `db`, parsed on the device (fasta_cuda.cu); *rejected = records dropped for a foreign character
+int db_fill_from_fasta(msv_db* db, const char* text, size_t bytes, size_t* rejected);
 } // namespace msv_detail

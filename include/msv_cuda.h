@@ -88,6 +88,10 @@ int msv_cuda_model_destroy(msv_model* model);
 int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane,
                             int* tensor_columns_per_lane, int* threads_per_cta, size_t* shared_bytes);
 
+/* geometry of the single-sequence latency kernel behind msv_cuda_score_sequence (a chain of warps over a thread-block
+ * cluster, msv_wave_kernels.cuh): columns per lane (0 = the model has no such plan), warps in the chain, CTAs in the cluster. */
+int msv_cuda_model_wave_geometry(const msv_model* model, int* columns_per_lane, int* warps, int* ctas);
+
 /* which launch plan a scan of the whole of `db` with `model` would use (introspection for tests and tuning): lanes per
  * sequence of the chosen kernel family (8, 32 or 128) and sequences in flight per CTA.  Does not launch anything. */
 int msv_cuda_model_plan(const msv_model* model, const msv_db* db, int* lanes_per_sequence, int* sequences_per_cta);
@@ -100,6 +104,20 @@ int msv_cuda_model_plan(const msv_model* model, const msv_db* db, int* lanes_per
 int msv_cuda_db_create(int device, const uint8_t* residues, const uint64_t* offsets, size_t n, msv_db** out);
 int msv_cuda_db_destroy(msv_db* db);
 int msv_cuda_db_info(const msv_db* db, size_t* n, uint64_t* total_residues, uint64_t* longest);
+
+/* FASTA text in HOST memory (e.g. an mmap'ed file) -> device-resident database, parsed ON the GPU: the raw text is
+ * uploaded (pageable memory is staged through pinned buffers by several host threads) and classified, encoded and cut
+ * into records by a handful of HBM-bound kernels (csrc/fasta_cuda.cu).  Record rules are those of the reference's
+ * FASTA_protein_sequences (data_readers/FASTA_protein_sequences.cpp:9-44): a line starting with '>' opens a record and is
+ * dropped, all other lines belong to the open record, a record with any character outside ACDEFGHIKLMNPQRSTVWY (a '\r'
+ * is one) is dropped WHOLE, text before the first header is ignored.  *rejected (may be NULL) = dropped records. */
+int msv_cuda_db_create_from_fasta(int device, const char* text, size_t bytes, msv_db** out, size_t* rejected);
+/* the same into an EXISTING handle (its device buffers only grow, so a handle can be refilled file after file without
+ * reallocating); on failure the handle is left empty */
+int msv_cuda_db_refill_from_fasta(msv_db* db, const char* text, size_t bytes, size_t* rejected);
+/* the packed form of a resident database back on the host (residues: total_residues bytes, offsets: n + 1 entries; either
+ * may be NULL) -- what the device-side FASTA parser is tested with */
+int msv_cuda_db_download(const msv_db* db, uint8_t* residues, uint64_t* offsets);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Scoring.  One kernel launch scores a resident database (msv_cuda_score_batch issues one launch per upload stage so
@@ -130,9 +148,16 @@ int msv_cuda_score_batch(msv_model* model, const uint8_t* residues, const uint64
  * then runs its cross-rank barrier (bench.py: the symmetric-memory barrier) before anybody reads the gathered array. */
 int msv_cuda_score_batch_gather(msv_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* const* gathered,
                                 int n_gathered, size_t first_index);
+/* FASTA text -> scores in one synchronous call: msv_cuda_db_create_from_fasta into the model's workspace, one scan, D2H.
+ * scores_host has room for `capacity` floats; *n_sequences (may be NULL) receives the number of sequences found -- when it
+ * exceeds `capacity` the call fails with MSV_ERR_INVALID_ARGUMENT and nothing is written. */
+int msv_cuda_score_fasta(msv_model* model, const char* text, size_t bytes, float* scores_host, size_t capacity, size_t* n_sequences,
+                         size_t* rejected);
 /* the CUDA device a model lives on */
 int msv_cuda_model_device(const msv_model* model, int* device);
-/* one sequence, synchronous: the body of MSV_HMM::parallel_run_on_sequence (reference MSV_HMM.cpp:269-430). */
+/* one sequence, synchronous: the body of MSV_HMM::parallel_run_on_sequence (reference MSV_HMM.cpp:269-430).  One launch
+ * of the wavefront kernel (the sequence travels in the kernel parameters when it is at most 3968 residues long, the
+ * result comes back through pinned host memory); a sequence that contains a real hit is re-scored by the exact kernel. */
 int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -728,3 +728,58 @@ def test_group_speculation_and_its_exact_pass(oracle, name, geometry, monkeypatc
     _cabi.launch_count(reset=True)
     assert ubits(db.score(model)).tolist() == ubits(want).tolist()
     assert _cabi.launch_count() == 1
+
+
+# ---- the single-sequence wavefront kernel (msv_wave_kernels.cuh) behind msv_cuda_score_sequence -------------------------
+@pytest.mark.parametrize("name,wave_k", [("100.hmm", None), ("500.hmm", None), ("1400.hmm", None), ("1400.hmm", "2"), ("1400.hmm", "4"),
+                                         ("1400.hmm", "6"), ("1400.hmm", "8"), ("1400.hmm", "12"), ("1400.hmm", "16"), ("2405.hmm", None),
+                                         ("2405.hmm", "4")])
+def test_single_sequence_wavefront_kernel(oracle, name, wave_k, monkeypatch):
+    """One sequence per call through the chain of warps: every chunk boundary (lengths around multiples of 4 and of the
+    16-chunk ring), the longest sequence that rides in the kernel parameters and the first that does not, long sequences
+    that wrap the ring many times; random sequences (speculation holds), consensus-derived hits (it fails: the exact kernel
+    re-scores) and everything in between -- reference bits every time."""
+    if wave_k:
+        monkeypatch.setenv("MSV_CUDA_WAVE_K", wave_k)
+    h = oracle.load_hmm(hmm_path(name))
+    model, table, tr3 = device_model(oracle, name)
+    geo = model.wave_geometry
+    assert geo["columns_per_lane"] == (int(wave_k) if wave_k else geo["columns_per_lane"]) and geo["columns_per_lane"] > 0
+    assert geo["warps"] * 32 * geo["columns_per_lane"] >= h["model_length"] - 1
+    rng = np.random.default_rng(h["model_length"])
+    consensus = np.argmax(h["match_emissions"][1:], axis=1).astype(np.uint8)
+    lengths = [0, 1, 2, 3, 4, 5, 7, 8, 9, 63, 64, 65, 66, 67, 68, 130, 255, 256, 257, 1000, 3500, 3967, 3968, 3969, 3970, 5000, 12001]
+    seqs = [rng.integers(0, 20, size=n, dtype=np.uint8) for n in lengths]
+    for n in (40, 200, 3500, 6000):  # hits: a consensus stretch somewhere inside
+        s = rng.integers(0, 20, size=n, dtype=np.uint8)
+        seg = min(n, 100, consensus.size)
+        at = int(rng.integers(0, n - seg + 1))
+        s[at:at + seg] = consensus[:seg]
+        seqs.append(s)
+    want = [oracle.score_codes(table, tr3, s) for s in seqs]
+    assert sum(w > 0 for w in want) >= 3  # the planted ones really are hits
+    for repeat in range(2):  # twice: the device-side accumulators must be clean again after every call
+        got = [model.score_sequence(s) for s in seqs]
+        assert [bits(v) for v in got] == [bits(v) for v in want], (name, wave_k, repeat)
+    with pytest.raises(_cabi.MsvCudaError) as err:
+        model.score_sequence(np.array([1, 2, 3, 4, 5, 6, 20, 7], np.uint8))
+    assert err.value.status == _cabi.MSV_ERR_BAD_RESIDUE and "position 6" in str(err.value)
+    with pytest.raises(_cabi.MsvCudaError):
+        bad = rng.integers(0, 20, size=5000, dtype=np.uint8)
+        bad[4999] = 200
+        model.score_sequence(bad)
+    assert bits(model.score_sequence(seqs[20])) == bits(want[20])  # and the next call is unaffected
+
+
+def test_single_sequence_wavefront_kernel_long_models(oracle):
+    """Synthetic models up to the on-chip limit (5631 columns): the chain then spans a whole 8-CTA cluster."""
+    for leng in (2816, 4096, 5631):
+        rng = np.random.default_rng(leng)
+        match = np.zeros((leng + 1, 20), np.float32)
+        match[1:] = rng.dirichlet(np.full(20, 0.4), size=leng).astype(np.float32)
+        table, tr3 = oracle.prepare(match)
+        model = msv.Model(_cabi.emission_table(match), *_cabi.model_transitions(leng + 1))
+        assert model.wave_geometry["columns_per_lane"] > 0 and model.wave_geometry["ctas"] <= 8
+        for n in (0, 5, 333, 2000):
+            s = rng.integers(0, 20, size=n, dtype=np.uint8)
+            assert bits(model.score_sequence(s)) == bits(oracle.score_codes(table, tr3, s)), (leng, n)
