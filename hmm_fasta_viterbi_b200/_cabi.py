@@ -100,7 +100,7 @@ lib.msv_cuda_db_create_from_fasta.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C
 lib.msv_cuda_db_refill_from_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
 lib.msv_cuda_db_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msv_cuda_score_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
-lib.msv_cuda_model_wave_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+lib.msv_cuda_model_wave_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
 lib.msv_cuda_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
 lib.msv_cuda_multi_destroy.argtypes = [C.c_void_p]
 lib.msv_cuda_multi_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
@@ -236,10 +236,11 @@ class Model:
 
     @property
     def wave_geometry(self) -> dict:
-        """Single-sequence latency kernel: columns per lane (0 = none), warps in the chain, CTAs in the cluster."""
-        k, w, c = C.c_int(), C.c_int(), C.c_int()
-        check(lib.msv_cuda_model_wave_geometry(self.handle, C.byref(k), C.byref(w), C.byref(c)))
-        return {"columns_per_lane": k.value, "warps": w.value, "ctas": c.value}
+        """Single-sequence latency kernels: CTAs of the diagonal-worker kernel (0 = model too long for it), and the chain
+        kernel's columns per lane (0 = none), warps in the chain, CTAs in the cluster."""
+        k, w, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib.msv_cuda_model_wave_geometry(self.handle, C.byref(k), C.byref(w), C.byref(c), C.byref(d)))
+        return {"columns_per_lane": k.value, "warps": w.value, "ctas": c.value, "diagonal_ctas": d.value}
 
     def plan(self, database: "Database") -> dict:
         """Launch plan a scan of `database` would use: kernel family (lanes per sequence) and sequences per CTA."""

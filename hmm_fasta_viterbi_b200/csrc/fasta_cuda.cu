@@ -40,18 +40,16 @@ constexpr uint32_t kTile = kThreads * kBytesPerThread;
 
 // letter -> code (order ACDEFGHIKLMNPQRSTVWY, reference MSV_HMM.cpp:29-31), 0xff for anything else
 __device__ __forceinline__ uint32_t residue_code(uint32_t c) {
-    // 'A'..'Y' -> 0..24, then a 25-entry table packed five bits per entry into two 64-bit words (31 = foreign)
+    // 'A'..'Y' -> 0..24, then a 25-entry table packed five bits per entry (31 = foreign) into 64-bit words of 12 entries
     const uint32_t i = c - 'A';
     if (i > 24u) return 0xffu;
-    //            A  B   C  D  E  F  G  H  I  J   K  L   M
-    // codes:     0  x   1  2  3  4  5  6  7  x   8  9   10
-    //            N   O  P   Q   R   S   T   U  V   W   X  Y
-    //            11  x  12  13  14  15  16  x  17  18  x  19
-    constexpr unsigned long long lo = 0ull | (31ull << 5) | (1ull << 10) | (2ull << 15) | (3ull << 20) | (4ull << 25) | (5ull << 30) |
-                                      (6ull << 35) | (7ull << 40) | (31ull << 45) | (8ull << 50) | (9ull << 55); // A..L (12 entries)
-    constexpr unsigned long long hi = 10ull | (11ull << 5) | (31ull << 10) | (12ull << 15) | (13ull << 20) | (14ull << 25) | (15ull << 30) |
-                                      (16ull << 35) | (31ull << 40) | (17ull << 45) | (18ull << 50) | (31ull << 55) | (19ull << 60); // M..Y
-    const uint32_t v = i < 12u ? static_cast<uint32_t>(lo >> (5u * i)) & 31u : static_cast<uint32_t>(hi >> (5u * (i - 12u))) & 31u;
+    //   A  B  C  D  E  F  G  H  I  J  K  L  |  M   N   O  P   Q   R   S   T   U  V   W   X  |  Y
+    //   0  x  1  2  3  4  5  6  7  x  8  9  |  10  11  x  12  13  14  15  16  x  17  18  x  |  19
+    constexpr unsigned long long a_to_l = 0ull | (31ull << 5) | (1ull << 10) | (2ull << 15) | (3ull << 20) | (4ull << 25) | (5ull << 30) |
+                                          (6ull << 35) | (7ull << 40) | (31ull << 45) | (8ull << 50) | (9ull << 55);
+    constexpr unsigned long long m_to_x = 10ull | (11ull << 5) | (31ull << 10) | (12ull << 15) | (13ull << 20) | (14ull << 25) | (15ull << 30) |
+                                          (16ull << 35) | (31ull << 40) | (17ull << 45) | (18ull << 50) | (31ull << 55);
+    const uint32_t v = i < 12u ? static_cast<uint32_t>(a_to_l >> (5u * i)) & 31u : i < 24u ? static_cast<uint32_t>(m_to_x >> (5u * (i - 12u))) & 31u : 19u;
     return v == 31u ? 0xffu : v;
 }
 

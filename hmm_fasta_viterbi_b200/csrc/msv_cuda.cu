@@ -55,13 +55,14 @@ struct Geometry {
     int variant = 0;        // 0: tensor-memory columns are each lane's lowest; 1: TMEM_AHEAD (they are the highest, loaded a row ahead)
     Scan_kernel fn_cj_same_exact = nullptr; // warp family: when fn_cj_same speculates B = N + move (and verifies), the kernel that never does
     Scan_kernel fn_group_spec = nullptr;    // lane-group family (G = 8): speculative scan; failures go to a second, exact launch
-    size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET) * (K - std::max(KT, 0)) * G * sizeof(float); }
+    // (four lanes per sequence: two interleaved copies of the table, see msv_scan_kernel)
+    size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET) * (K - std::max(KT, 0)) * std::max(G, KT < 0 ? 8 : G) * sizeof(float); }
 };
 
 // speculative lane-group scan: ahead of the exact one by 15 % at K = 16 (LENG 100) and 2 % at K = 28, behind it from K = 40 up
 // (profiles/r01/sweep_group_spec.txt), so it exists for the short models only
 template <int G, int K> constexpr Scan_kernel group_spec_kernel() {
-    if constexpr (G == 8 && K <= 28) return msv::msv_scan_group_spec_kernel<G, K, threads_for(K)>;
+    if constexpr ((G == 8 && K <= 28) || G == 4) return msv::msv_scan_group_spec_kernel<G, K, threads_for(K)>;
     else return nullptr;
 }
 template <int G, int K> constexpr Geometry generic_entry() {
@@ -114,13 +115,16 @@ template <int K, int KT, int T> constexpr Geometry warp_entry_ahead() {
     X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) X(A, 76)  \
     X(A, 80) X(A, 84) X(A, 88)
 #ifdef MSV_QUICK_BUILD // development aid: only what a 1400-column model needs, so that a kernel experiment compiles in seconds
-const Geometry g_geometries[] = {generic_entry<32, 44>(), warp_entry_ahead<44, 24, 512>(), warp_entry<44, 16>(), quad_entry<12, 8>()
+const Geometry g_geometries[] = {generic_entry<32, 44>(), warp_entry_ahead<44, 24, 512>(), warp_entry<44, 16>(), quad_entry<12, 8>(),
+                                 generic_entry<4, 28>(), generic_entry<8, 16>()
 #ifdef MSV_QUICK_EXTRA
                                  , MSV_QUICK_EXTRA
 #endif
 };
 #else
-const Geometry g_geometries[] = {MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(MSV_GENERIC, 16) MSV_FOR_EACH_K(MSV_GENERIC, 32)
+#define MSV_FOR_EACH_K_TO_56(X, A)                                                                                     \
+    X(A, 4) X(A, 8) X(A, 12) X(A, 16) X(A, 20) X(A, 24) X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56)
+const Geometry g_geometries[] = {MSV_FOR_EACH_K_TO_56(MSV_GENERIC, 4) MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(MSV_GENERIC, 16) MSV_FOR_EACH_K(MSV_GENERIC, 32)
                                      MSV_WARP(0, 4) MSV_WARP(0, 8) MSV_WARP(8, 8) MSV_WARP(8, 12) MSV_WARP(8, 16) MSV_WARP(8, 20)
                                          MSV_WARP(16, 16) MSV_WARP(16, 20) MSV_WARP(24, 24) MSV_FOR_EACH_K_FROM_24(MSV_WARP, 16)
                                              MSV_FOR_EACH_K_FROM_28(MSV_WARP, 24) MSV_WARP(0, 44) MSV_WARP(8, 44)
@@ -197,6 +201,12 @@ const Geometry* choose_octet_geometry(size_t columns) {
     const int K = std::max(4, round_up4((columns + 1 + 7) / 8)); // 8*K > columns
     return (columns >= 64 && K <= 56) ? find_geometry(8, K, -1) : nullptr;
 }
+// Four lanes per sequence (eight sequences per warp) for the shortest models: less padding (LENG 100: 112 instead of 128
+// slots) and the per-row bookkeeping of a warp is shared by eight sequences.
+const Geometry* choose_narrow_geometry(size_t columns) {
+    const int K = std::max(4, round_up4((columns + 1 + 3) / 4)); // 4*K > columns
+    return (columns >= 32 && K <= 56) ? find_geometry(4, K, -1) : nullptr;
+}
 
 // Four warps per sequence: the plan for few/long sequences and for models beyond one warp's registers.
 const Geometry* choose_quad_geometry(size_t columns) {
@@ -247,6 +257,7 @@ struct msv_model {
     };
     Plan bulk;  // many sequences: one warp per sequence (or whatever MSV_CUDA_GEOMETRY forces)
     Plan octet; // short models and enough sequences to balance 4x more slots: eight lanes per sequence (may be absent)
+    Plan narrow; // the shortest models, eight times more slots: four lanes per sequence (may be absent)
     Plan quad;  // few or very long sequences, single-sequence calls: four warps per sequence (may be absent)
     bool forced = false; // MSV_CUDA_GEOMETRY was given: always use `bulk`
     float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
@@ -268,6 +279,11 @@ struct msv_model {
         cudaStream_t stream = nullptr;
         uint32_t tag = 0;
         const Wave_kernels* kernels = nullptr;
+        // the communication-free variant (one thread per diagonal phase, msv_diag_kernel): the reference-layout table with
+        // every row extended by its first four columns; used when table + 4 bytes per row fit one SM's shared memory
+        float* d_diag_table = nullptr;
+        uint32_t diag_period = 0, diag_ctas = 0;
+        size_t diag_table_bytes = 0;
     } wave;
 };
 
@@ -516,8 +532,20 @@ Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, 
     const bool few = count < 4 * bulk_slots && residues >= 1000 * static_cast<uint64_t>(count) && db->h_lengths.size() == db->n &&
                      model->bulk.geo->G == 32;
     if (!few) {
-        if (model->octet.geo && 4 * (residues / (sms * max_slots(model->octet))) >= 3 * std::max<uint64_t>(db->longest, 1))
-            return {&model->octet, max_slots(model->octet)};
+        // Lane-group plans (short models) have 4x / 8x more slots than the warp plan, and a slot scans a sequence at a
+        // quarter / an eighth of a warp's speed: with few sequences per slot the scan ends when the longest sequence does.
+        // So the slot count is CUT (fewer CTA threads: fewer, faster slots) until every slot gets 1.2x the rows of the longest
+        // sequence, down to a third of the maximum; the SM keeps most of its throughput on the way.  Measured on B200
+        // (profiles/r02/short_model_sweep_v1.jsonl, 100.hmm x 100 k sequences, four lanes per sequence): 192 slots per CTA
+        // 5.0 TCUPS, 96: 6.3, 64: 6.6, 48: 5.9; with 1 M sequences every slot count is balanced and the maximum wins (7.5).
+        // Four lanes per sequence beat eight wherever both exist (100.hmm 7.5 vs 6.2, 200.hmm 8.4 vs 7.6 TCUPS at 1 M).
+        for (const msv_model::Plan* plan : {&model->narrow, &model->octet}) {
+            if (!plan->geo) continue;
+            const size_t per_warp = 32 / static_cast<size_t>(plan->geo->G);
+            const size_t most = max_slots(*plan), least = std::max(per_warp, most / 3 / per_warp * per_warp);
+            for (size_t slots = most; slots >= least; slots -= per_warp)
+                if (10 * (residues / (sms * slots)) >= 12 * std::max<uint64_t>(db->longest, 1)) return {plan, slots};
+        }
         if (model->quad.geo && count < 2 * bulk_slots) return {&model->quad, max_slots(model->quad)};
         return {&model->bulk, max_slots(model->bulk)};
     }
@@ -579,32 +607,17 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     if (ctas == 1) slots = std::min(slots, count); // do not launch slots that would find the queue empty
     const int threads = static_cast<int>(std::max<size_t>(32, (slots * threads_per_slot + 31) / 32 * 32));
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
-    // lane-group plan: speculative scan + exact pass over the sequences whose speculation failed (two launches; the second
-    // reads its sequence count from device memory and usually finds a handful)
-    const bool group_speculation = geo->fn_group_spec && cj_same && residues / count <= msv::kSpeculationMaxLength / 2 &&
-                                   count >= 4096 && !std::getenv("MSV_CUDA_NO_SPECULATION");
-    if (group_speculation) {
-        unsigned int* redo_count = db->d_queue + kMaxChunks + queue_slot;
-        unsigned int* redo_head = db->d_queue + 2 * kMaxChunks + queue_slot;
-        MSV_CUDA_TRY(cudaMemsetAsync(redo_count, 0, sizeof(unsigned int), stream));
-        MSV_CUDA_TRY(cudaMemsetAsync(redo_head, 0, sizeof(unsigned int), stream));
-        p.redo_list = db->d_redo + first;
-        p.redo_count = redo_count;
+    const bool group_speculation = geo->fn_group_spec && cj_same && residues / count <= 2048 && count >= 4096 &&
+                                   !std::getenv("MSV_CUDA_NO_SPECULATION");
+    if (group_speculation) { // lane groups with speculative rows; a sequence whose speculation fails is repeated exactly in the kernel
         geo->fn_group_spec<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
-        ++g_launches;
-        MSV_CUDA_TRY(cudaGetLastError());
-        p.order = p.redo_list;
-        p.n_device = redo_count;
-        p.queue_head = redo_head;
-        geo->fn_cj_same<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
         ++g_launches;
         MSV_CUDA_TRY(cudaGetLastError());
         return MSV_OK;
     }
     Scan_kernel kernel = cj_same ? geo->fn_cj_same : geo->fn;
-    // databases of long sequences (config 5: 10-35 k residues each) would mostly be scanned twice by the speculative rows
-    const bool long_sequences = residues / count > msv::kSpeculationMaxLength / 2;
-    if (cj_same && geo->fn_cj_same_exact && (long_sequences || std::getenv("MSV_CUDA_NO_SPECULATION"))) kernel = geo->fn_cj_same_exact;
+    // (the speculative rows checkpoint every 64 rows, so a hit costs one block whatever the sequence length: no length limit)
+    if (cj_same && geo->fn_cj_same_exact && std::getenv("MSV_CUDA_NO_SPECULATION")) kernel = geo->fn_cj_same_exact;
     kernel<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
     ++g_launches;
     MSV_CUDA_TRY(cudaGetLastError());
@@ -693,6 +706,7 @@ namespace {
 void wave_release(msv_model* model) {
     auto& w = model->wave;
     cudaFree(w.d_table);
+    cudaFree(w.d_diag_table);
     cudaFree(w.d_accumulator);
     cudaFree(w.d_residues);
     if (w.h_result) cudaFreeHost(w.h_result);
@@ -740,6 +754,22 @@ cudaError_t wave_build(msv_model* model, const float* emission_scores, size_t co
         err = cudaHostGetDevicePointer(&w.d_result, w.h_result, 0);
     }
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking);
+    // the diagonal-worker kernel: [residue][P + 4] floats, P = model_length; it needs 80 (P + 4) bytes of shared memory
+    const size_t diag_bytes = static_cast<size_t>(MSV_ALPHABET) * (model_length + 4) * sizeof(float);
+    if (err == cudaSuccess && model_length >= 8 && diag_bytes + 4096 <= w.shared_limit && !std::getenv("MSV_CUDA_NO_DIAGONAL")) {
+        std::vector<float> extended(static_cast<size_t>(MSV_ALPHABET) * (model_length + 4));
+        for (int res = 0; res < MSV_ALPHABET; ++res)
+            for (size_t col = 0; col < model_length + 4; ++col)
+                extended[res * (model_length + 4) + col] = emission_scores[res * model_length + col % model_length];
+        err = cudaMalloc(&w.d_diag_table, diag_bytes);
+        if (err == cudaSuccess) err = cudaMemcpy(w.d_diag_table, extended.data(), diag_bytes, cudaMemcpyHostToDevice);
+        for (const void* fn : {reinterpret_cast<const void*>(msv::msv_diag_kernel<true>), reinterpret_cast<const void*>(msv::msv_diag_kernel<false>)})
+            if (err == cudaSuccess) err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(w.shared_limit));
+        w.diag_period = static_cast<uint32_t>(model_length);
+        w.diag_table_bytes = diag_bytes;
+        const size_t diag_warps = (model_length + 31) / 32;
+        w.diag_ctas = static_cast<uint32_t>((diag_warps + msv::kWaveWarpsPerCta - 1) / msv::kWaveWarpsPerCta);
+    }
     if (err == cudaSuccess)
         err = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernels->with_inline_residues), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(w.shared_limit));
@@ -754,9 +784,12 @@ cudaError_t wave_build(msv_model* model, const float* emission_scores, size_t co
 int wave_score(msv_model* model, const uint8_t* residues, size_t length, float* score, bool* rescore) {
     auto& w = model->wave;
     *rescore = false;
-    // every CTA keeps one word per row of the sequence next to its table slice; a sequence too long for that (tens of
+    const size_t row_bytes = (length + 3) / 4 * 16 + 32; // one word per row of the sequence, next to the table
+    // first choice: one thread per diagonal phase, no communication (needs the whole table in one SM's shared memory)
+    const bool diagonal = w.d_diag_table && w.diag_table_bytes + row_bytes <= w.shared_limit;
+    // every CTA of the chain kernel keeps the same words next to its table slice; a sequence too long for that (tens of
     // thousands of residues) goes to the four-warp kernel
-    const size_t shared_bytes = w.shared_bytes + (length + 3) / 4 * 16 + 16;
+    const size_t shared_bytes = diagonal ? w.diag_table_bytes + row_bytes : w.shared_bytes + row_bytes;
     if (shared_bytes > w.shared_limit) {
         *rescore = true;
         return MSV_OK;
@@ -785,11 +818,27 @@ int wave_score(msv_model* model, const uint8_t* residues, size_t length, float* 
     config.attrs = &cluster;
     config.numAttrs = 1;
 
+    msv::Diag_params dp{};
+    if (diagonal) {
+        dp.table = w.d_diag_table;
+        dp.accumulator = w.d_accumulator;
+        dp.result = w.d_result;
+        dp.length = p.length;
+        dp.period = w.diag_period;
+        dp.tag = p.tag;
+        dp.tr_B_Mk = p.tr_B_Mk;
+        dp.tr_E_J = p.tr_E_J;
+        dp.loop = p.loop;
+        dp.move = p.move;
+        config.gridDim = dim3(w.diag_ctas);
+        config.numAttrs = 0; // independent CTAs: no cluster
+    }
     if (length <= msv::kWaveInlineBytes) {
         msv::Wave_inline_residues block; // the sequence rides in the kernel parameters: one launch, no copy
         block.words[(length ? length - 1 : 0) / 4] = 0;
         if (length) std::memcpy(block.words, residues, length);
-        MSV_CUDA_TRY(cudaLaunchKernelEx(&config, w.kernels->with_inline_residues, p, block));
+        if (diagonal) MSV_CUDA_TRY(cudaLaunchKernelEx(&config, msv::msv_diag_kernel<true>, dp, block));
+        else MSV_CUDA_TRY(cudaLaunchKernelEx(&config, w.kernels->with_inline_residues, p, block));
     } else {
         const size_t padded = (length + 3) / 4 * 4;
         if (padded > w.capacity) {
@@ -806,8 +855,9 @@ int wave_score(msv_model* model, const uint8_t* residues, size_t length, float* 
         std::memcpy(w.h_staging, residues, length);
         std::memset(w.h_staging + length, 0, padded - length);
         MSV_CUDA_TRY(cudaMemcpyAsync(w.d_residues, w.h_staging, padded, cudaMemcpyHostToDevice, w.stream));
-        p.residues = w.d_residues;
-        MSV_CUDA_TRY(cudaLaunchKernelEx(&config, w.kernels->with_device_residues, p, msv::Wave_no_residues{}));
+        p.residues = dp.residues = w.d_residues;
+        if (diagonal) MSV_CUDA_TRY(cudaLaunchKernelEx(&config, msv::msv_diag_kernel<false>, dp, msv::Wave_no_residues{}));
+        else MSV_CUDA_TRY(cudaLaunchKernelEx(&config, w.kernels->with_device_residues, p, msv::Wave_no_residues{}));
     }
     ++g_launches;
     // the kernel writes the result into pinned host memory; poll it (a stream query every so often notices a failed launch)
@@ -977,7 +1027,9 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
     //   tensor-memory part : [residue][lane g][KT]          j = 0 .. KT-1
     const auto build = [&](const Geometry* geo, msv_model::Plan& plan) -> cudaError_t {
         const int G = geo->G, K = geo->K, KT = std::max(geo->KT, 0), KS = K - KT;
-        const size_t shared_floats = static_cast<size_t>(MSV_ALPHABET) * KS * G;
+        const int copies = (geo->KT < 0 && G < 8) ? 8 / G : 1; // lane groups narrower than a quarter-warp: interleaved copies
+        const int R = G * copies;                               // lane slots per quad row of the shared-memory table
+        const size_t shared_floats = static_cast<size_t>(MSV_ALPHABET) * KS * R;
         const size_t floats = shared_floats + static_cast<size_t>(MSV_ALPHABET) * KT * G;
         std::vector<float> laid(std::max<size_t>(floats, 4), -std::numeric_limits<float>::infinity());
         const auto emission = [&](int res, int g, int j) {
@@ -989,7 +1041,8 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         for (int res = 0; res < MSV_ALPHABET; ++res)
             for (int g = 0; g < G; ++g) {
                 for (int js = 0; js < KS; ++js)
-                    laid[((static_cast<size_t>(res) * (KS / 4) + js / 4) * G + g) * 4 + js % 4] = emission(res, g, shared_first + js);
+                    for (int copy = 0; copy < copies; ++copy)
+                        laid[((static_cast<size_t>(res) * (KS / 4) + js / 4) * R + copy * G + g) * 4 + js % 4] = emission(res, g, shared_first + js);
                 for (int jt = 0; jt < KT; ++jt)
                     laid[shared_floats + (static_cast<size_t>(res) * G + g) * KT + jt] = emission(res, g, tensor_first + jt);
             }
@@ -1011,11 +1064,15 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         const cudaError_t quad_err = build(quad_geo, model->quad);
         if (!bulk_geo) err = quad_err; // the quad plan is optional unless it is the only one
     }
-    if (err == cudaSuccess && bulk_geo && !forced)
-        if (const Geometry* octet_geo = choose_octet_geometry(columns)) (void)build(octet_geo, model->octet); // optional
+    if (err == cudaSuccess && bulk_geo && !forced) {
+        if (const Geometry* octet_geo = choose_octet_geometry(columns)) (void)build(octet_geo, model->octet);    // optional
+        if (const Geometry* narrow_geo = choose_narrow_geometry(columns)) (void)build(narrow_geo, model->narrow); // optional
+        (void)cudaGetLastError();
+    }
     if (err != cudaSuccess || (!model->bulk.geo && !model->quad.geo)) {
         cudaFree(model->bulk.d_table);
         cudaFree(model->octet.d_table);
+        cudaFree(model->narrow.d_table);
         cudaFree(model->quad.d_table);
         delete model;
         (void)cudaGetLastError();
@@ -1042,6 +1099,7 @@ int msv_cuda_model_destroy(msv_model* model) {
         wave_release(model);
         cudaFree(model->bulk.d_table);
         cudaFree(model->octet.d_table);
+        cudaFree(model->narrow.d_table);
         cudaFree(model->quad.d_table);
     }
     delete model;
@@ -1060,11 +1118,12 @@ int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int
     return MSV_OK;
 }
 
-int msv_cuda_model_wave_geometry(const msv_model* model, int* columns_per_lane, int* warps, int* ctas) {
+int msv_cuda_model_wave_geometry(const msv_model* model, int* columns_per_lane, int* warps, int* ctas, int* diagonal_ctas) {
     if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
     if (columns_per_lane) *columns_per_lane = model->wave.kernels ? model->wave.K : 0;
     if (warps) *warps = static_cast<int>(model->wave.warps);
     if (ctas) *ctas = static_cast<int>(model->wave.ctas);
+    if (diagonal_ctas) *diagonal_ctas = model->wave.d_diag_table ? static_cast<int>(model->wave.diag_ctas) : 0;
     return MSV_OK;
 }
 

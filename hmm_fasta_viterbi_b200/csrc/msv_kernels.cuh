@@ -45,12 +45,16 @@ namespace msv {
 // sequences of the warp, which is what makes this family the faster one for short models.
 // The host guarantees G*K > model columns: the last column of a group's last lane is -inf padding, so the rotating
 // shuffle hands lane 0 of each group the -inf of the dummy column M0 (same trick as in the warp kernel below).
+// G = 4: a quarter-warp (the unit in which an LDS.128 is served) holds TWO groups, whose residues differ; the table is
+// therefore stored as two interleaved copies ([residue][quad][copy][lane][4]: copy 0 in banks 0-15, copy 1 in banks 16-31),
+// even groups read copy 0 and odd groups copy 1, and every access stays conflict-free whatever the residues are.
 template <int G, int K, int THREADS, bool CJ_SAME>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params p) {
-    static_assert(G == 8 || G == 16 || G == 32, "lanes per sequence");
+    static_assert(G == 4 || G == 8 || G == 16 || G == 32, "lanes per sequence");
     static_assert(K % 4 == 0 && K >= 4 && K <= kMaxColumnsPerLane, "columns per lane");
-    constexpr uint32_t ROW_BYTES = (K / 4) * G * 16; // bytes per residue row of the table
-    constexpr uint32_t QUAD_BYTES = G * 16;
+    constexpr int LANES_PER_QUAD_ROW = G < 8 ? 8 : G;
+    constexpr uint32_t QUAD_BYTES = LANES_PER_QUAD_ROW * 16;
+    constexpr uint32_t ROW_BYTES = (K / 4) * QUAD_BYTES; // bytes per residue row of the table
     constexpr uint32_t COPY_CHUNK = 32768;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
     const int gl = lane & (G - 1);
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
     const int left_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1)); // rotate inside the group
-    const uint32_t tab_lane = smem_u32(smem_raw) + gl * 16;
+    const uint32_t tab_lane = smem_u32(smem_raw) + (lane & (LANES_PER_QUAD_ROW - 1)) * 16;
     const float NEG_INF = __int_as_float(0xff800000);
     const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
     const uint32_t n_sequences = p.n_device ? *p.n_device : p.n; // the exact pass after a speculative scan reads its count here
@@ -173,15 +177,21 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
 // ---- the lane-group scan with SPECULATIVE rows (see msv_scan_warp_kernel for the argument) ----------------------------
 // For short models the per-row bookkeeping of the exact row -- a group-wide max by shuffles, the J and B maxima -- costs as
 // much as the cells.  While J <= N, B is N + move and needs none of it: the row is cells + one FMNMX3 chain + this lane's
-// share of J.  Four (G = 8) sequences advance per warp instruction, four rows per residue word.  Verification is one group
-// vote when a sequence retires; a sequence that fails it is appended to `redo_list` and scanned by msv_scan_kernel in a
-// second launch that reads its count from `redo_count` (same table, same database, exact rows).  tr_E_C == tr_E_J only.
+// share of J.  32/G sequences advance per warp instruction, four rows per residue word.  Verification is one group vote
+// when a sequence retires.  A sequence that fails it (it contains a real hit: ~0.2 % of random sequences) is scanned again
+// AT ONCE by the same group with the exact row -- sequences are handed out longest first, so a long sequence that has to be
+// repeated is repeated early, not as a lonely tail after everybody else has finished (an earlier version collected the
+// failures in a list for a second launch, whose run time was the longest failed sequence at single-warp speed).  While any
+// group of a warp is in its exact pass the whole warp executes exact rows; they are valid for speculating groups too
+// (a lane's share of J only grows towards the true J, and B = max(N, J) + move is N + move for as long as their speculation
+// holds).  tr_E_C == tr_E_J only.  G = 4 uses two interleaved copies of the table (see msv_scan_kernel).
 template <int G, int K, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const Scan_params p) {
-    static_assert(G == 8 || G == 16, "lanes per sequence");
+    static_assert(G == 4 || G == 8 || G == 16, "lanes per sequence");
     static_assert(K % 4 == 0 && K >= 4 && K <= kMaxColumnsPerLane, "columns per lane");
-    constexpr uint32_t ROW_BYTES = (K / 4) * G * 16;
-    constexpr uint32_t QUAD_BYTES = G * 16;
+    constexpr int LANES_PER_QUAD_ROW = G < 8 ? 8 : G; // G = 4: two copies of the table side by side, one per neighbouring group
+    constexpr uint32_t QUAD_BYTES = LANES_PER_QUAD_ROW * 16;
+    constexpr uint32_t ROW_BYTES = (K / 4) * QUAD_BYTES;
     constexpr uint32_t COPY_CHUNK = 32768;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -204,26 +214,27 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
     const int gl = lane & (G - 1);
     const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
     const int left_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1)); // rotate inside the group
-    const uint32_t tab_lane = smem_u32(smem_raw) + gl * 16;
+    const uint32_t tab_lane = smem_u32(smem_raw) + (lane & (LANES_PER_QUAD_ROW - 1)) * 16;
     const float NEG_INF = __int_as_float(0xff800000);
     const float tBMk = p.tr_B_Mk, tEJ = p.tr_E_J;
 
     float m[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) m[j] = NEG_INF;
-    float J = NEG_INF, N = 0.0f, B = NEG_INF, loop = 0.0f, move = 0.0f; // J: this LANE's share of J
+    float J = NEG_INF, N = 0.0f, B = NEG_INF, loop = 0.0f, move = 0.0f; // J: this LANE's share of J (the whole J in an exact pass)
 
-    uint32_t remaining = 0, idx = 0;
-    bool active = false, done = false;
+    uint32_t remaining = 0, idx = 0, len = 0;
+    uint64_t begin = 0;
+    bool active = false, done = false, exact = false;
     // residue window of the group's sequence: the next residue is byte `phase/8` of the 64-bit value (whi:wlo)
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.residues);
     uint32_t wlo = 0, whi = 0, phase = 0;
 
-    auto row = [&](const uint32_t x) {
+    const auto cells = [&](const uint32_t x, float& e) {
         const uint32_t erow = tab_lane + x * ROW_BYTES;
         const float bt = B + tBMk;
         const float left = __shfl_sync(0xffffffffu, m[K - 1], left_lane);
-        float e = NEG_INF;
+        e = NEG_INF;
 #pragma unroll
         for (int q = K / 4 - 1; q >= 0; --q) {
             const float4 ev = lds128(erow + q * QUAD_BYTES);
@@ -235,23 +246,57 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
             e = fmaxf(fmaxf(e, m[j + 3]), m[j + 2]);
             e = fmaxf(fmaxf(e, m[j + 1]), m[j]);
         }
+    };
+    const auto row = [&](const uint32_t x) {
+        float e;
+        cells(x, e);
         J = fmaxf(J + loop, e + tEJ);
         N = N + loop;
         B = N + move; // = max(N, J) + move while J <= N -- verified when the sequence retires
+    };
+    const auto exact_row = [&](const uint32_t x) {
+        float e;
+        cells(x, e);
+#pragma unroll
+        for (int d = G / 2; d > 0; d >>= 1) e = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, d)); // E of the group (MSV_HMM.cpp:104)
+        J = fmaxf(J + loop, e + tEJ);                                                              // MSV_HMM.cpp:107
+        N = N + loop;
+        B = fmaxf(N, J) + move; // MSV_HMM.cpp:110
+    };
+    const auto start_sequence = [&] { // (re)start the scan of sequence `idx` at its first row
+#pragma unroll
+        for (int j = 0; j < K; ++j) m[j] = NEG_INF;
+        J = NEG_INF;
+        N = 0.0f;
+        B = move;
+        const uint32_t mis = static_cast<uint32_t>(begin) & 3u;
+        wp = reinterpret_cast<const uint32_t*>(p.residues + (begin - mis));
+        wlo = __ldg(wp);
+        whi = __ldg(wp + 1);
+        wp += 2;
+        phase = 8u * mis;
+        remaining = len;
     };
 
     for (;;) {
         // ---- retire finished sequences, pull new ones (group-uniform control flow) ----
         while (remaining == 0 && !done) {
             if (active) {
-                // if J overtook N at any row, this lane's or a neighbour's share still is >= N now (both decay by + loop)
-                const bool suspect = __any_sync(gmask, J >= N);
-                float best = J;
+                if (exact) {
+                    if (gl == 0) store_score(p, idx, J + move); // MSV_HMM.cpp:112 (every lane holds the whole J)
+                    exact = false;
+                } else {
+                    // if J overtook N at any row, this lane's or a neighbour's share still is >= N now (both decay by + loop)
+                    const bool suspect = __any_sync(gmask, J >= N);
+                    float best = J;
 #pragma unroll
-                for (int d = G / 2; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(gmask, best, d));
-                if (gl == 0) {
-                    if (suspect) p.redo_list[atomicAdd(p.redo_count, 1u)] = idx;
-                    else store_score(p, idx, best + move);
+                    for (int d = G / 2; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(gmask, best, d));
+                    if (suspect && len > 0) { // the speculation did not hold: the same sequence again, exactly, right now
+                        exact = true;
+                        start_sequence();
+                        continue;
+                    }
+                    if (gl == 0) store_score(p, idx, best + move);
                 }
                 active = false;
             }
@@ -265,23 +310,12 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
                 break;
             }
             idx = __ldg(p.order + ticket);
-            const uint64_t begin = __ldg(p.offsets + idx);
-            const uint32_t len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
+            begin = __ldg(p.offsets + idx);
+            len = static_cast<uint32_t>(__ldg(p.offsets + idx + 1) - begin);
             const float2 tr = __ldg(p.length_tr + len);
             loop = tr.x;
             move = tr.y;
-#pragma unroll
-            for (int j = 0; j < K; ++j) m[j] = NEG_INF;
-            J = NEG_INF;
-            N = 0.0f;
-            B = move;
-            const uint32_t mis = static_cast<uint32_t>(begin) & 3u;
-            wp = reinterpret_cast<const uint32_t*>(p.residues + (begin - mis));
-            wlo = __ldg(wp);
-            whi = __ldg(wp + 1);
-            wp += 2;
-            phase = 8u * mis;
-            remaining = len;
+            start_sequence();
             active = true;
         }
 
@@ -292,6 +326,21 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
         if (!done) remaining -= steps;
         const uint32_t advance = done ? 0u : 1u;
 
+        if (__any_sync(0xffffffffu, exact && !done)) { // some group of this warp is in its exact pass: exact rows for everybody
+#pragma unroll 1
+            for (uint32_t t = steps; t > 0; --t) {
+                const uint32_t x = __funnelshift_r(wlo, whi, phase) & 0xffu;
+                phase += 8u;
+                if (phase == 32u) {
+                    phase = 0;
+                    wlo = whi;
+                    whi = __ldg(wp);
+                    wp += advance;
+                }
+                exact_row(x);
+            }
+            continue;
+        }
 #pragma unroll 1
         for (uint32_t t = steps >> 2; t > 0; --t) { // one residue word = four rows
             const uint32_t word = __funnelshift_r(wlo, whi, phase);
@@ -353,7 +402,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
 //     speculation held.  Verification is one vote per SEQUENCE: if J[i] > N[i] at some row then j >= N from that row on
 //     in the lane that saw it (j and N decay by the same + loop), so "some lane ends with j >= N" catches every
 //     sequence whose B ever differed; those are scanned again with the exact row.  Same bits, always.
-constexpr uint32_t kSpeculationMaxLength = 4096;
+constexpr uint32_t kSpeculationBlockRows = 64; // rows between two checkpoints of the speculative rows (a multiple of 16)
 
 template <int K, int KT, int THREADS, bool CJ_SAME, bool TMEM_AHEAD = false, bool SPECULATE = false>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_params p) {
@@ -513,9 +562,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         uint32_t word = __funnelshift_r(w0, w1, shift);
         // (an empty sequence's "first residue" is a foreign byte: clamp, as for every prefetch index below)
         if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + min(word & 0xffu, static_cast<uint32_t>(kAlphabet - 1)) * KT, te);
-        // long sequences are likely enough to contain a hit that speculating on them would mostly mean scanning them twice
-        const bool speculate = SPEC && len <= kSpeculationMaxLength;
-        const uint32_t quads = (!SPEC || speculate) ? len >> 2 : 0u;
+        const uint32_t quads = len >> 2;
         // 4 rows (one residue word) per loop iteration, 8 or 16 where B200 sweeps showed a gain (+1..4 %, +10 % at K = 4;
         // profiles/r01/sweep_models_v6_row_unroll.jsonl, sweep_force_unroll2.txt).  It is not monotone in K -- the
         // instruction scheduler's luck -- and the longest bodies stop fitting the instruction cache (-10 % at K = 76).
@@ -526,45 +573,78 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
 #else
         constexpr int WORD_UNROLL = K == 4 ? 4 : EIGHT_ROWS ? 2 : 1;
 #endif
+        // SPECULATION WITH CHECKPOINTS.  The speculative rows run in blocks of kSpeculationBlockRows rows; before a block the
+        // row state (m[], this lane's share of J, N) is parked in local memory, after it ONE vote asks whether J has overtaken
+        // N.  If it has, only that block is lost: the state of its first row is restored -- it is exact, the vote before it
+        // passed -- the lanes' shares are combined into J, and the rest of the sequence runs with the exact row.  A hit
+        // therefore costs at most one block of rows plus the slower exact rows behind it, whatever the sequence length
+        // (before: the whole sequence was scanned twice, and sequences beyond 4096 rows did not speculate at all).
+        [[maybe_unused]] volatile float parked[SPEC ? K + 2 : 1]; // volatile: really in local memory, not 46 more registers
+        uint32_t block_first = 0; // first residue word of the block at hand
+        bool overtaken = false;
+        for (;;) {
+            const uint32_t block_end = SPEC ? min(quads, block_first + kSpeculationBlockRows / 4) : quads;
+            if constexpr (SPEC) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) parked[j] = m[j];
+                parked[K] = J;
+                parked[K + 1] = N;
+            }
 #pragma unroll WORD_UNROLL
-        for (uint32_t i = 0; i < quads; ++i) {
-            const uint32_t ahead = __funnelshift_r(w1, w2, shift);
-            w1 = w2;
-            w2 = __ldg(wp);
-            ++wp;
-            const uint32_t x0 = __byte_perm(word, 0, 0x4440), x1 = __byte_perm(word, 0, 0x4441);
-            const uint32_t x2 = __byte_perm(word, 0, 0x4442), x3 = __byte_perm(word, 0, 0x4443);
-            row(x0, x1);
-            row(x1, x2);
-            row(x2, x3);
-            // the row after the last one of a sequence is somebody else's byte (the next sequence's, or memory that a later
-            // upload stage has not filled or validated yet): it only feeds the tensor-memory PREFETCH, whose result is then
-            // dropped, but it must never become a TMEM address outside the table -- hence the clamp to a real residue code
-            row(x3, min(__byte_perm(ahead, 0, 0x4440), static_cast<uint32_t>(kAlphabet - 1)));
-            word = ahead;
-        }
+            for (uint32_t i = block_first; i < block_end; ++i) {
+                const uint32_t ahead = __funnelshift_r(w1, w2, shift);
+                w1 = w2;
+                w2 = __ldg(wp);
+                ++wp;
+                const uint32_t x0 = __byte_perm(word, 0, 0x4440), x1 = __byte_perm(word, 0, 0x4441);
+                const uint32_t x2 = __byte_perm(word, 0, 0x4442), x3 = __byte_perm(word, 0, 0x4443);
+                row(x0, x1);
+                row(x1, x2);
+                row(x2, x3);
+                // the row after the last one of a sequence is somebody else's byte (the next sequence's, or memory that a later
+                // upload stage has not filled or validated yet): it only feeds the tensor-memory PREFETCH, whose result is then
+                // dropped, but it must never become a TMEM address outside the table -- hence the clamp to a real residue code
+                row(x3, min(__byte_perm(ahead, 0, 0x4440), static_cast<uint32_t>(kAlphabet - 1)));
+                word = ahead;
+            }
+            const bool last_block = block_end == quads;
+            if (last_block) {
 #pragma unroll 1
-        for (uint32_t r = (!SPEC || speculate) ? len & 3u : 0u; r > 0; --r) {
-            row(word & 0xffu, min((word >> 8) & 0xffu, static_cast<uint32_t>(kAlphabet - 1)));
-            word >>= 8;
+                for (uint32_t r = len & 3u; r > 0; --r) {
+                    row(word & 0xffu, min((word >> 8) & 0xffu, static_cast<uint32_t>(kAlphabet - 1)));
+                    word >>= 8;
+                }
+            }
+            if constexpr (SPEC) {
+                if (__any_sync(0xffffffffu, J >= N)) {
+                    overtaken = true;
+                    break;
+                }
+            }
+            if (last_block) break;
+            block_first = block_end;
         }
         if constexpr (SPEC) {
-            if (!speculate || __any_sync(0xffffffffu, J >= N)) {
-                // J may have overtaken N at some row, where B was then not N + move: scan this sequence again, exactly
+            if (overtaken) {
+                // J overtook N inside this block, where B was then not N + move: back to the block's first row, exactly from there
                 if constexpr (TMEM_AHEAD && KT > 0) tmem_wait<KT>(te); // retire the request made by the last speculative row
 #pragma unroll
-                for (int j = 0; j < K; ++j) m[j] = NEG_INF;
-                J = NEG_INF, N = 0.0f, B = move;
-                const uint8_t* rp = p.residues + begin;
-                uint32_t x = __ldg(rp);
+                for (int j = 0; j < K; ++j) m[j] = parked[j];
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(J) : "f"(parked[K])); // the lanes' shares -> J
+                N = parked[K + 1];
+                B = N + move; // J < N here: the vote before this block passed
+                const uint32_t first_row = 4u * block_first;
+                const uint8_t* rp = p.residues + begin + first_row;
+                uint32_t x = first_row < len ? __ldg(rp) : 0u;
                 if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + x * KT, te);
 #pragma unroll 1
-                for (uint32_t i = 0; i < len; ++i) {
+                for (uint32_t i = first_row; i < len; ++i) {
                     // the byte after the last residue is another sequence's or padding: prefetch index only, clamped (see above)
-                    const uint32_t x_next = min(static_cast<uint32_t>(__ldg(rp + i + 1)), static_cast<uint32_t>(kAlphabet - 1));
+                    const uint32_t x_next = min(static_cast<uint32_t>(__ldg(rp + (i - first_row) + 1)), static_cast<uint32_t>(kAlphabet - 1));
                     any_row(Exact_row{}, x, x_next);
                     x = x_next;
                 }
+                if constexpr (TMEM_AHEAD && KT > 0) tmem_wait<KT>(te);
             } else {
                 asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(J) : "f"(J));
             }

@@ -189,8 +189,8 @@ msv_wave_kernel(const __grid_constant__ Wave_params p,
     const bool invalid = bad_code != 0;
 
     float J = NEG_INF, N = 0.0f;
+    if (my_warps > 0) mbarrier_wait(&table_ready, 0); // (unconditionally: nobody leaves while a bulk copy into its shared memory is in flight)
     if (in_chain && !invalid) {
-        mbarrier_wait(&table_ready, 0);
         const uint32_t tab = smem_u32(smem_raw) + warp * WARP_TABLE_BYTES + lane * 8;
         const float tBMk = p.tr_B_Mk, tEJ = p.tr_E_J, loop = p.loop, move = p.move;
         const bool has_left = g > 0, has_right = g + 1 < p.warps;
@@ -206,19 +206,30 @@ msv_wave_kernel(const __grid_constant__ Wave_params p,
         for (int j = 0; j < K; ++j) m[j] = NEG_INF; // MSV_HMM.cpp:86
         float B = move;                             // MSV_HMM.cpp:96-97 (N = 0 above)
 
+        // Emissions are fetched one chunk (four rows) AHEAD of their use: with one warp per scheduler nothing else hides the
+        // shared-memory latency, and the in-order issue would stall on every row otherwise.
+        struct Chunk_emissions {
+            float2 e[4][K / 2];
+        };
+        const auto fetch = [&](Chunk_emissions& into, const uint4 o) {
+            const uint32_t at[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < K / 2; ++q)
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(into.e[r][q].x), "=f"(into.e[r][q].y) : "r"(tab + at[r] + q * 256));
+        };
         // one row: `from_left` = last column of my left neighbour's previous row (-inf for the first block: the dummy column M0)
-        const auto row = [&](const uint32_t row_offset, const float from_left) {
-            const uint32_t erow = tab + row_offset;
+        const auto row = [&](const float2 (&ev)[K / 2], const float from_left) {
             const float bt = B + tBMk; // MSV_HMM.cpp:103, B -> M_k entry
             const float up = __shfl_up_sync(0xffffffffu, m[K - 1], 1);
             const float left = lane == 0 ? from_left : up;
             float e = NEG_INF;
 #pragma unroll
             for (int q = K / 2 - 1; q >= 0; --q) { // highest column first: every cell reads its not-yet-overwritten left neighbour
-                const float2 ev = lds64(erow + q * 256);
                 const int j = 2 * q;
-                m[j + 1] = ev.y + fmaxf(m[j], bt);
-                m[j] = ev.x + fmaxf(j ? m[j > 0 ? j - 1 : 0] : left, bt);
+                m[j + 1] = ev[q].y + fmaxf(m[j], bt);
+                m[j] = ev[q].x + fmaxf(j ? m[j > 0 ? j - 1 : 0] : left, bt);
                 e = fmaxf(fmaxf(e, m[j + 1]), m[j]); // MSV_HMM.cpp:104
             }
             J = fmaxf(J + loop, e + tEJ); // this lane's share of J (MSV_HMM.cpp:107); combined once, after the last row
@@ -237,10 +248,17 @@ msv_wave_kernel(const __grid_constant__ Wave_params p,
         if (incoming_chunks > 0) incoming = lds128_volatile_u32(slot_of(0));
         float previous_last = NEG_INF; // "row 0": nothing enters from the left before the first row
         uint32_t taken_seen = 0;
-        uint4 offsets = words ? row_offsets[0] : make_uint4(0, 0, 0, 0), offsets_next = words > 1 ? row_offsets[1] : make_uint4(0, 0, 0, 0);
+        const uint32_t offsets_at = smem_u32(row_offsets);
+        const auto offsets_of = [&](uint32_t c) { return lds128_volatile_u32(offsets_at + c * 16u); };
+        Chunk_emissions ahead;
+        if (words) fetch(ahead, offsets_of(0));
+        uint4 offsets_next = words > 1 ? offsets_of(1) : make_uint4(0, 0, 0, 0);
 
 #pragma unroll 2
         for (uint32_t c = 0; c < chunks; ++c) {
+            const Chunk_emissions now = ahead;
+            if (c + 1 < words) fetch(ahead, offsets_next);
+            if (c + 2 < words) offsets_next = offsets_of(c + 2);
             uint4 cur = incoming;
             if (has_left) {
                 while (is_empty(cur)) cur = lds128_volatile_u32(slot_of(c));
@@ -255,16 +273,13 @@ msv_wave_kernel(const __grid_constant__ Wave_params p,
             if (has_right) {
                 while (c >= taken_seen + kWaveSlots) taken_seen = lds_volatile_u32(my_taken);
             }
-            const uint4 o = offsets;
-            offsets = offsets_next;
-            if (c + 2 < words) offsets_next = *reinterpret_cast<const uint4*>(smem_raw + TABLE_BYTES + (c + 2) * 16u);
-            row(o.x, previous_last);
+            row(now.e[0], previous_last);
             const float b0 = m[K - 1];
-            row(o.y, __uint_as_float(cur.x));
+            row(now.e[1], __uint_as_float(cur.x));
             const float b1 = m[K - 1];
-            row(o.z, __uint_as_float(cur.y));
+            row(now.e[2], __uint_as_float(cur.y));
             const float b2 = m[K - 1];
-            row(o.w, __uint_as_float(cur.z));
+            row(now.e[3], __uint_as_float(cur.z));
             previous_last = __uint_as_float(cur.w);
             if (has_right && lane == 31) store_remote_v4(right_ring + (c % kWaveSlots), b0, b1, b2, m[K - 1]);
         }
@@ -278,13 +293,12 @@ msv_wave_kernel(const __grid_constant__ Wave_params p,
             if (has_right) {
                 while (c >= taken_seen + kWaveSlots) taken_seen = lds_volatile_u32(my_taken);
             }
-            const uint32_t o[3] = {offsets.x, offsets.y, offsets.z};
             const float from_left[3] = {previous_last, __uint_as_float(cur.x), __uint_as_float(cur.y)};
             float b[3] = {NEG_INF, NEG_INF, NEG_INF};
 #pragma unroll
             for (uint32_t r = 0; r < 3; ++r) {
                 if (r < rest) {
-                    row(o[r], from_left[r]);
+                    row(ahead.e[r], from_left[r]);
                     b[r] = m[K - 1];
                 }
             }
@@ -317,6 +331,151 @@ msv_wave_kernel(const __grid_constant__ Wave_params p,
     }
     // nobody leaves while a neighbour may still store into its shared memory
     cluster_sync_all();
+}
+
+// =====================================================================================================================
+// The same single sequence with NO communication at all: one THREAD per diagonal phase.
+//
+// With the speculative row the only dependency is M[i][k] <- M[i-1][k-1]: cells on different diagonals never meet.  Worker
+// w (one thread) walks down the rows 1 .. L and, at row i, owns column (i - 1 - w) mod P of the P = LENG + 1 columns
+// 0 .. LENG -- i.e. it follows one diagonal to the last column, wraps to column 0 and follows the next one.  Column 0 is the
+// reference's dummy column M0, whose emission is -inf (MSV_HMM.cpp:38-45 with the zero-filled row 0 of match_emissions,
+// Profile_HMM.cpp:110-111): passing through it resets the worker's value to -inf exactly as M[i][0] = -inf does in the
+// reference, so there is no wrap logic in the arithmetic.  P workers cover every column of every row.  Each worker keeps
+// its own share of J and its own copy of N / B (running sums, the same in every thread); at the end the shares are combined
+// like in the chain kernel above.  Per row and thread: one LDS (all lanes of a warp read consecutive columns of the same
+// residue's row: conflict-free, and the table is the reference's own [residue][column] layout), two maxima, six adds.
+// The critical path is the row count times one max + one add: ~20 us for 3500 rows, whatever the model length, on
+// ceil(P / 128) SMs with one warp per scheduler.  Needs the whole table (80 bytes per column) plus 4 bytes per row in one
+// SM's shared memory: models up to ~2650 columns; longer ones use the chain kernel.
+// =====================================================================================================================
+struct Diag_params {
+    const float* table;         // [residue][P + 4]: the reference's table, every row extended by its own first four columns
+    const uint8_t* residues;    // device memory (when not inline)
+    Wave_accumulator* accumulator;
+    Wave_result* result;
+    uint32_t length;
+    uint32_t period;            // P = model_length = LENG + 1
+    uint32_t tag;
+    float tr_B_Mk, tr_E_J, loop, move;
+};
+
+template <bool INLINE>
+__global__ void __launch_bounds__(kWaveWarpsPerCta * 32, 1)
+msv_diag_kernel(const __grid_constant__ Diag_params p,
+                const __grid_constant__ std::conditional_t<INLINE, Wave_inline_residues, Wave_no_residues> inl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t table_ready;
+    __shared__ uint32_t bad_code;
+
+    const int lane = threadIdx.x & 31;
+    const uint32_t row_bytes = (p.period + 4u) * 4u;    // one residue's emissions, with the four wrapped columns
+    const uint32_t table_bytes = kAlphabet * row_bytes; // a multiple of 16
+    const float NEG_INF = __int_as_float(0xff800000);
+
+    if (threadIdx.x == 0) {
+        mbarrier_init(&table_ready, 1);
+        bad_code = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbarrier_expect_tx(&table_ready, table_bytes);
+        for (uint32_t at = 0; at < table_bytes; at += 32768)
+            tma_bulk_load(smem_raw + at, reinterpret_cast<const unsigned char*>(p.table) + at, min(32768u, table_bytes - at), &table_ready);
+    }
+    // while the table is in flight: validate the residues and turn them into row offsets (one word per row, chunks of four)
+    const uint32_t words = (p.length + 3) / 4;
+    uint4* row_offsets = reinterpret_cast<uint4*>(smem_raw + (table_bytes + 15u) / 16u * 16u);
+    {
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(p.residues);
+        uint32_t bad = 0;
+        for (uint32_t c = threadIdx.x; c < words; c += blockDim.x) {
+            uint32_t w;
+            if constexpr (INLINE) w = inl.words[c];
+            else w = __ldg(gw + c);
+            if (c == words - 1 && (p.length & 3u)) w &= (1u << (8u * (p.length & 3u))) - 1u;
+            bad |= (((w & 0x7f7f7f7fu) + 0x6c6c6c6cu) | w) & 0x80808080u; // some byte >= 20
+            row_offsets[c] = make_uint4((w & 0xffu) * row_bytes, ((w >> 8) & 0xffu) * row_bytes, ((w >> 16) & 0xffu) * row_bytes, (w >> 24) * row_bytes);
+        }
+        if (bad) bad_code = 1;
+    }
+    __syncthreads();
+    const bool invalid = bad_code != 0;
+
+    float J = NEG_INF, N = 0.0f;
+    mbarrier_wait(&table_ready, 0); // (also when the residues are invalid: nobody leaves while a bulk copy into its shared memory is in flight)
+    if (!invalid) {
+        const float tBMk = p.tr_B_Mk, tEJ = p.tr_E_J, loop = p.loop, move = p.move;
+        const uint32_t period_bytes = p.period * 4u;
+        // worker w is on column (i - 1 - w) mod P at row i: at the first row on column (P - w mod P) mod P
+        const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) % p.period; // (surplus lanes of the last warp repeat early workers)
+        uint32_t column_bytes = w ? (p.period - w) * 4u : 0u;
+        const uint32_t tab = smem_u32(smem_raw);
+        const uint32_t offsets_at = smem_u32(row_offsets);
+        float y = NEG_INF, B = move; // MSV_HMM.cpp:86, 96-97
+
+        const auto fetch = [&](float (&e)[4], const uint4 o, const uint32_t at) { // the four emissions of a chunk: columns at .. at + 3
+            const uint32_t base = tab + at;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e[0]) : "r"(base + o.x));
+            asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(e[1]) : "r"(base + o.y));
+            asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(e[2]) : "r"(base + o.z));
+            asm volatile("ld.shared.f32 %0, [%1+12];" : "=f"(e[3]) : "r"(base + o.w));
+        };
+        const auto row = [&](const float e) {
+            const float bt = B + tBMk;    // MSV_HMM.cpp:103, B -> M_k entry
+            y = e + fmaxf(y, bt);         // MSV_HMM.cpp:103: M[i][k] from M[i-1][k-1]; e = -inf on the dummy column resets the diagonal
+            J = fmaxf(J + loop, y + tEJ); // this thread's share of J (MSV_HMM.cpp:104,107)
+            N = N + loop;                 // MSV_HMM.cpp:109
+            B = N + move;                 // MSV_HMM.cpp:110 while J <= N -- verified after the last row
+        };
+        const auto advance = [&](uint32_t at) { // four columns on, modulo P
+            at += 16u;
+            return at >= period_bytes ? at - period_bytes : at;
+        };
+        const auto offsets_of = [&](uint32_t c) { return lds128_volatile_u32(offsets_at + c * 16u); };
+
+        const uint32_t chunks = p.length / 4, rest = p.length & 3u;
+        float ahead[4] = {NEG_INF, NEG_INF, NEG_INF, NEG_INF};
+        if (words) fetch(ahead, offsets_of(0), column_bytes);
+        column_bytes = advance(column_bytes);
+        uint4 offsets_next = words > 1 ? offsets_of(1) : make_uint4(0, 0, 0, 0);
+#pragma unroll 2
+        for (uint32_t c = 0; c < chunks; ++c) {
+            const float e0 = ahead[0], e1 = ahead[1], e2 = ahead[2], e3 = ahead[3];
+            if (c + 1 < words) fetch(ahead, offsets_next, column_bytes); // emissions one chunk ahead of their use
+            column_bytes = advance(column_bytes);
+            if (c + 2 < words) offsets_next = offsets_of(c + 2);
+            row(e0);
+            row(e1);
+            row(e2);
+            row(e3);
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < 3; ++r)
+            if (r < rest) row(ahead[r]);
+    }
+
+    // ---- combine: max of the threads' shares of J, did the speculation hold, and hand the result to the host ----
+    const bool suspect = __any_sync(0xffffffffu, J >= N);
+    float Jw;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(Jw) : "f"(J));
+    if (lane == 0) {
+        atomicMax(&p.accumulator->best, ordered_bits(Jw));
+        const unsigned int status = (suspect && !invalid ? 1u : 0u) | (invalid ? 2u : 0u);
+        if (status) atomicOr(&p.accumulator->status, status);
+        __threadfence();
+        if (atomicAdd(&p.accumulator->finished, 1u) == gridDim.x * (blockDim.x / 32) - 1) { // every warp's contribution is in
+            __threadfence();
+            const float best = from_ordered_bits(atomicExch(&p.accumulator->best, 0u));
+            const unsigned int verdict = atomicExch(&p.accumulator->status, 0u);
+            atomicExch(&p.accumulator->finished, 0u);
+            volatile Wave_result* out = p.result;
+            out->score = best + p.move; // MSV_HMM.cpp:112 (C == J: tr_E_C == tr_E_J)
+            out->status = verdict;
+            __threadfence_system();
+            out->tag = p.tag;
+        }
+    }
 }
 
 } // namespace msv

@@ -88,9 +88,11 @@ int msv_cuda_model_destroy(msv_model* model);
 int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int* columns_per_lane,
                             int* tensor_columns_per_lane, int* threads_per_cta, size_t* shared_bytes);
 
-/* geometry of the single-sequence latency kernel behind msv_cuda_score_sequence (a chain of warps over a thread-block
- * cluster, msv_wave_kernels.cuh): columns per lane (0 = the model has no such plan), warps in the chain, CTAs in the cluster. */
-int msv_cuda_model_wave_geometry(const msv_model* model, int* columns_per_lane, int* warps, int* ctas);
+/* geometry of the single-sequence latency kernels behind msv_cuda_score_sequence (msv_wave_kernels.cuh).  First choice: one
+ * thread per diagonal phase, no communication, the whole table in every CTA's shared memory -- *diagonal_ctas CTAs of 128
+ * threads (0 = the model is too long for it).  Otherwise a chain of warps over a thread-block cluster: columns per lane
+ * (0 = the model has no such plan either), warps in the chain, CTAs in the cluster.  Any pointer may be NULL. */
+int msv_cuda_model_wave_geometry(const msv_model* model, int* columns_per_lane, int* warps, int* ctas, int* diagonal_ctas);
 
 /* which launch plan a scan of the whole of `db` with `model` would use (introspection for tests and tuning): lanes per
  * sequence of the chosen kernel family (8, 32 or 128) and sequences in flight per CTA.  Does not launch anything. */
@@ -156,8 +158,8 @@ int msv_cuda_score_fasta(msv_model* model, const char* text, size_t bytes, float
 /* the CUDA device a model lives on */
 int msv_cuda_model_device(const msv_model* model, int* device);
 /* one sequence, synchronous: the body of MSV_HMM::parallel_run_on_sequence (reference MSV_HMM.cpp:269-430).  One launch
- * of the wavefront kernel (the sequence travels in the kernel parameters when it is at most 3968 residues long, the
- * result comes back through pinned host memory); a sequence that contains a real hit is re-scored by the exact kernel. */
+ * of a latency kernel (the sequence travels in the kernel parameters when it is at most 3968 residues long, the result
+ * comes back through pinned host memory); a sequence that contains a real hit is re-scored by the exact kernel. */
 int msv_cuda_score_sequence(msv_model* model, const uint8_t* residues, size_t length, float* score);
 
 /* ---------------------------------------------------------------------------------------------------------------

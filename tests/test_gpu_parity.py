@@ -97,7 +97,7 @@ def test_homologous_sequences_exercise_the_J_state(oracle):
     assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
 
 
-@pytest.mark.parametrize("geometry", ["8,4", "8,16", "8,64", "16,8", "16,32", "16,88", "32,4", "32,20", "32,24", "32,44",
+@pytest.mark.parametrize("geometry", ["4,8", "4,28", "4,52", "8,4", "8,16", "8,64", "16,8", "16,32", "16,88", "32,4", "32,20", "32,24", "32,44",
                                        "32,56", "32,60", "32,88",
                                        # warp kernels: shared memory + KT tensor-memory columns per lane
                                        "32,4,0", "32,8,0", "32,8,8", "32,20,8", "32,24,16", "32,28,16", "32,44,0", "32,44,8",
@@ -225,6 +225,9 @@ def test_launch_planner_choices(oracle):
     many_db = msv.Database(many.residues, many.offsets)
     assert big.plan(many_db) == {"lanes_per_sequence": 32, "sequences_per_cta": 16}      # bulk: a warp each, 16 warps per SM
     assert short.plan(many_db)["lanes_per_sequence"] == 8                                # short model, many sequences: 8 lanes each
+    shortest, _, _ = device_model(oracle, "100.hmm")
+    plan = shortest.plan(many_db)                                                        # the shortest models: 4 lanes each, and
+    assert plan["lanes_per_sequence"] == 4 and 64 <= plan["sequences_per_cta"] < 192     # fewer slots than the maximum at this size
     titin = msv.Packed_sequences.synthetic_long_uniform(2048, 2405, 10_000, 35_000)     # config 5: fewer sequences than warp slots
     plan = big.plan(msv.Database(titin.residues, titin.offsets))
     assert plan["lanes_per_sequence"] == 32 and plan["sequences_per_cta"] in (8, 12)     # a warp each at reduced occupancy
@@ -695,14 +698,15 @@ def test_speculation_falls_back_exactly_on_hits(oracle, name, monkeypatch):
     assert ubits(model.score_batch(long_codes, long_offsets)).tolist() == ubits(want[-12:]).tolist()
 
 
-@pytest.mark.parametrize("name,geometry", [("100.hmm", "8,16"), ("200.hmm", "8,28")])
+@pytest.mark.parametrize("name,geometry", [("100.hmm", "8,16"), ("200.hmm", "8,28"), ("100.hmm", "4,28"), ("200.hmm", "4,52")])
 def test_group_speculation_and_its_exact_pass(oracle, name, geometry, monkeypatch):
-    """Eight lanes per sequence, speculative rows: sequences whose speculation fails (consensus-derived hits) are appended
-    to a list on the device and scanned by a second, exact launch that reads its count from device memory."""
+    """Eight / four lanes per sequence, speculative rows: a sequence whose speculation fails (consensus-derived hits) is
+    scanned again at once, exactly, by the same lane group inside the same launch; while it is, the other groups of its warp
+    execute exact rows too."""
     monkeypatch.setenv("MSV_CUDA_GEOMETRY", geometry)
     h = oracle.load_hmm(hmm_path(name))
     model, table, tr3 = device_model(oracle, name)
-    assert model.geometry["lanes_per_sequence"] == 8
+    assert model.geometry["lanes_per_sequence"] == int(geometry.split(",")[0])
     leng = h["model_length"] - 1
     consensus = np.argmax(h["match_emissions"][1:], axis=1).astype(np.uint8)
     rng = np.random.default_rng(leng + 1)
@@ -721,7 +725,7 @@ def test_group_speculation_and_its_exact_pass(oracle, name, geometry, monkeypatc
     db = msv.Database(codes, offsets)
     _cabi.launch_count(reset=True)
     assert ubits(db.score(model)).tolist() == ubits(want).tolist()
-    assert _cabi.launch_count() == 2  # speculative scan + exact pass
+    assert _cabi.launch_count() == 1  # one launch: sequences whose speculation fails are repeated exactly inside it
     assert ubits(db.score(model)).tolist() == ubits(want).tolist()  # counters are reset between scans
     assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
     monkeypatch.setenv("MSV_CUDA_NO_SPECULATION", "1")
@@ -739,11 +743,13 @@ def test_single_sequence_wavefront_kernel(oracle, name, wave_k, monkeypatch):
     16-chunk ring), the longest sequence that rides in the kernel parameters and the first that does not, long sequences
     that wrap the ring many times; random sequences (speculation holds), consensus-derived hits (it fails: the exact kernel
     re-scores) and everything in between -- reference bits every time."""
-    if wave_k:
+    if wave_k:  # the chain kernel with this many columns per lane; otherwise the default, the diagonal-worker kernel
         monkeypatch.setenv("MSV_CUDA_WAVE_K", wave_k)
+        monkeypatch.setenv("MSV_CUDA_NO_DIAGONAL", "1")
     h = oracle.load_hmm(hmm_path(name))
     model, table, tr3 = device_model(oracle, name)
     geo = model.wave_geometry
+    assert (geo["diagonal_ctas"] == 0) == bool(wave_k)
     assert geo["columns_per_lane"] == (int(wave_k) if wave_k else geo["columns_per_lane"]) and geo["columns_per_lane"] > 0
     assert geo["warps"] * 32 * geo["columns_per_lane"] >= h["model_length"] - 1
     rng = np.random.default_rng(h["model_length"])
@@ -780,6 +786,7 @@ def test_single_sequence_wavefront_kernel_long_models(oracle):
         table, tr3 = oracle.prepare(match)
         model = msv.Model(_cabi.emission_table(match), *_cabi.model_transitions(leng + 1))
         assert model.wave_geometry["columns_per_lane"] > 0 and model.wave_geometry["ctas"] <= 8
+        assert model.wave_geometry["diagonal_ctas"] == 0  # beyond one SM's shared memory: the chain kernel is in charge
         for n in (0, 5, 333, 2000):
             s = rng.integers(0, 20, size=n, dtype=np.uint8)
             assert bits(model.score_sequence(s)) == bits(oracle.score_codes(table, tr3, s)), (leng, n)

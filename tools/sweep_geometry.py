@@ -26,6 +26,7 @@ def main() -> None:
     ap.add_argument("--geometries", nargs="+", default=["default"])
     ap.add_argument("--long", action="store_true", help="config-5 style database (L ~ U[10000, 35000])")
     ap.add_argument("--check", type=int, default=200, help="sequences compared with the oracle per geometry")
+    ap.add_argument("--slots", nargs="+", type=int, default=[0], help="sequences in flight per CTA (MSV_CUDA_BULK_SLOTS; 0 = the plan's own)")
     args = ap.parse_args()
 
     import torch
@@ -68,20 +69,27 @@ def main() -> None:
         except Exception as e:  # noqa: BLE001
             print(json.dumps({"geometry": geo, "error": str(e)}))
             continue
-        for _ in range(2):
-            db.score_device(model, scores, stream.cuda_stream)
-        torch.cuda.synchronize()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record(stream)
-        for _ in range(args.steps):
-            db.score_device(model, scores, stream.cuda_stream)
-        t1.record(stream)
-        torch.cuda.synchronize()
-        ms = t0.elapsed_time(t1) / args.steps
-        got = scores.cpu().numpy()[sample]
-        bad = int((got.view(np.uint32) != want.view(np.uint32)).sum())
-        print(json.dumps({"geometry": geo, "chosen": model.geometry, "ms": round(ms, 3), "gcups": round(cells / ms / 1e6, 1),
-                          "cells_per_clk_per_sm": round(cells / (ms * 1e-3) / 148 / 1.965e9, 2), "mismatches": bad}), flush=True)
+        for slots in args.slots:
+            if slots:
+                os.environ["MSV_CUDA_BULK_SLOTS"] = str(slots)
+            else:
+                os.environ.pop("MSV_CUDA_BULK_SLOTS", None)
+            for _ in range(2):
+                db.score_device(model, scores, stream.cuda_stream)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(stream)
+            for _ in range(args.steps):
+                db.score_device(model, scores, stream.cuda_stream)
+            t1.record(stream)
+            torch.cuda.synchronize()
+            ms = t0.elapsed_time(t1) / args.steps
+            got = scores.cpu().numpy()[sample]
+            bad = int((got.view(np.uint32) != want.view(np.uint32)).sum())
+            print(json.dumps({"model": args.model, "sequences": args.sequences, "geometry": geo, "slots": slots, "plan": model.plan(db),
+                              "chosen": model.geometry, "ms": round(ms, 3), "gcups": round(cells / ms / 1e6, 1),
+                              "cells_per_clk_per_sm": round(cells / (ms * 1e-3) / 148 / 1.965e9, 2), "mismatches": bad}), flush=True)
+        os.environ.pop("MSV_CUDA_BULK_SLOTS", None)
         model.close()
 
 
