@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmsv_cuda.so")
+LIB_PATH = os.environ.get("MSV_CUDA_LIBRARY") or os.path.join(_PKG, "libmsv_cuda.so")  # (the override is a kernel-development aid)
 
 MSV_OK = 0
 MSV_ERR_INVALID_ARGUMENT = -1
@@ -33,6 +33,7 @@ DECLARED_SYMBOLS = (
     "msv_cuda_launch_count",
     "msv_cuda_score_batch_gather", "msv_cuda_model_device", "msv_cuda_model_wave_geometry",
     "msv_cuda_db_create_from_fasta", "msv_cuda_db_refill_from_fasta", "msv_cuda_db_download", "msv_cuda_score_fasta",
+    "msv_cuda_db_msv_filter", "msv_cuda_db_viterbi_subset_device", "msv_cuda_db_viterbi_filter_survivors",
     "msv_cuda_multi_create", "msv_cuda_multi_destroy", "msv_cuda_multi_score_batch", "msv_cuda_multi_gathered",
     "msv_host_viterbi_transitions", "msv_cuda_viterbi_model_create", "msv_cuda_viterbi_model_destroy",
     "msv_cuda_viterbi_model_geometry", "msv_cuda_db_viterbi_device", "msv_cuda_db_viterbi", "msv_cuda_db_viterbi_filter", "msv_cuda_viterbi_batch",
@@ -96,6 +97,11 @@ lib.msv_cuda_db_viterbi_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.
 lib.msv_cuda_viterbi_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
 lib.msv_cuda_score_batch_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_int, C.c_size_t]
 lib.msv_cuda_model_device.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+lib.msv_cuda_db_msv_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.POINTER(C.c_size_t)]
+lib.msv_cuda_db_viterbi_subset_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+lib.msv_cuda_db_viterbi_filter_survivors.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                     C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
 lib.msv_cuda_db_create_from_fasta.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
 lib.msv_cuda_db_refill_from_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
 lib.msv_cuda_db_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

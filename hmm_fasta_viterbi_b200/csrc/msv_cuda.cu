@@ -304,6 +304,7 @@ int db_release(msv_db* db) {
     cudaFree(db->d_hist);
     cudaFree(db->d_queue);
     cudaFree(db->d_first_bad);
+    if (db->filter_scratch && db->filter_scratch_free) db->filter_scratch_free(db->filter_scratch);
     if (db->copy_stream) {
         cudaStreamDestroy(db->copy_stream);
         cudaStreamDestroy(db->compute_stream);

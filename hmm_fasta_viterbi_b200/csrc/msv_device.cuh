@@ -32,6 +32,8 @@ struct Scan_params {
     uint32_t* redo_list;
     unsigned int* redo_count;
     const unsigned int* n_device;
+    // sequences whose speculation failed in this scan (statistics for the host's choice of the speculation mode); may be NULL
+    unsigned int* speculation_failures;
 };
 
 // the one store per sequence: local result plus, for the fused gather, the same 4 bytes into every peer's array

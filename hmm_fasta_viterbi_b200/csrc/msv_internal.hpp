@@ -65,6 +65,10 @@ struct msv_db {
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     cudaEvent_t stage_copied[kMaxChunks] = {};
     cudaEvent_t reserved = nullptr;
+    // filter stages kept on the device (filter_cuda.cu): scratch + the survivors of the last MSV filter stage
+    void* filter_scratch = nullptr;
+    void (*filter_scratch_free)(void*) = nullptr;
+    size_t n_survivors = 0;
 };
 
 namespace msv_detail {

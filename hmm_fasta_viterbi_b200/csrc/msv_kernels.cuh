@@ -402,11 +402,21 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
 //     speculation held.  Verification is one vote per SEQUENCE: if J[i] > N[i] at some row then j >= N from that row on
 //     in the lane that saw it (j and N decay by the same + loop), so "some lane ends with j >= N" catches every
 //     sequence whose B ever differed; those are scanned again with the exact row.  Same bits, always.
-constexpr uint32_t kSpeculationBlockRows = 64; // rows between two checkpoints of the speculative rows (a multiple of 16)
+#ifndef MSV_SPEC_BLOCK_ROWS
+#define MSV_SPEC_BLOCK_ROWS 64
+#endif
 
-template <int K, int KT, int THREADS, bool CJ_SAME, bool TMEM_AHEAD = false, bool SPECULATE = false>
+constexpr uint32_t kSpeculationBlockRows = MSV_SPEC_BLOCK_ROWS; // rows between two checkpoints of the speculative rows (a multiple of 16)
+
+// SPECULATE: 0 = exact rows only; 1 = speculate on the whole sequence, verify once at its end, scan it again exactly when the
+// vote fails; 2 = speculate in blocks with checkpoints (below).  Mode 1 is the faster one when hits are rare (the compiler
+// schedules its plain loop 2-3 % better: 10.08 vs 9.85 TCUPS at K = 44, profiles/r02/variant_sweep_v3.txt) and loses a whole
+// extra pass per hit; mode 2 loses one block per hit.  The host picks per launch from the share of failed speculations it
+// observed in the previous scan of the same database (Scan_params::speculation_failures) and from the sequence lengths.
+template <int K, int KT, int THREADS, bool CJ_SAME, bool TMEM_AHEAD = false, int SPECULATE = 0>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_params p) {
-    constexpr bool SPEC = SPECULATE && CJ_SAME;
+    constexpr bool SPEC = SPECULATE != 0 && CJ_SAME;
+    constexpr bool CHECKPOINTS = SPECULATE == 2 && CJ_SAME;
     static_assert(KT >= 0 && KT <= 24 && KT % 2 == 0, "TMEM columns per lane");
     constexpr int KS = K - KT;
     static_assert(K % 2 == 0 && KS >= 0 && KS % 4 == 0 && K <= kMaxColumnsPerLane, "columns per lane");
@@ -419,7 +429,10 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
     __shared__ __align__(8) uint64_t table_ready;
     __shared__ uint32_t tmem_base_slot;
 
-    const int lane = threadIdx.x & 31;
+    int lane = threadIdx.x & 31;
+    // opaque to the compiler from here on: at this kernel's register limit it otherwise RE-READS SR_TID (a ~25-clock S2R) inside
+    // the row loop to rebuild the lane's table address and shuffle source instead of keeping them in registers
+    asm volatile("" : "+r"(lane));
     const int warp = threadIdx.x >> 5;
 
     // never index the table with an unvalidated residue code: the validation kernel precedes this launch on the stream
@@ -562,6 +575,65 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         uint32_t word = __funnelshift_r(w0, w1, shift);
         // (an empty sequence's "first residue" is a foreign byte: clamp, as for every prefetch index below)
         if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + min(word & 0xffu, static_cast<uint32_t>(kAlphabet - 1)) * KT, te);
+        if constexpr (!CHECKPOINTS) {
+        // long sequences are likely enough to contain a hit that speculating on them would mostly mean scanning them twice
+        const bool speculate = SPEC && len <= 4096u;
+        const uint32_t quads = (!SPEC || speculate) ? len >> 2 : 0u;
+        // 4 rows (one residue word) per loop iteration, 8 or 16 where B200 sweeps showed a gain (+1..4 %, +10 % at K = 4;
+        // profiles/r01/sweep_models_v6_row_unroll.jsonl, sweep_force_unroll2.txt).  It is not monotone in K -- the
+        // instruction scheduler's luck -- and the longest bodies stop fitting the instruction cache (-10 % at K = 76).
+        constexpr bool EIGHT_ROWS = K == 20 || K == 30 || K == 32 || K == 36 || K == 42 || K == 44 || K == 52 || K == 54 || K == 58 ||
+                                    K == 60 || K == 68;
+#ifdef MSV_FORCE_UNROLL // development aid (with MSV_QUICK_BUILD)
+        constexpr int WORD_UNROLL = MSV_FORCE_UNROLL;
+#else
+        constexpr int WORD_UNROLL = K == 4 ? 4 : EIGHT_ROWS ? 2 : 1;
+#endif
+#pragma unroll WORD_UNROLL
+        for (uint32_t i = 0; i < quads; ++i) {
+            const uint32_t ahead = __funnelshift_r(w1, w2, shift);
+            w1 = w2;
+            w2 = __ldg(wp);
+            ++wp;
+            const uint32_t x0 = __byte_perm(word, 0, 0x4440), x1 = __byte_perm(word, 0, 0x4441);
+            const uint32_t x2 = __byte_perm(word, 0, 0x4442), x3 = __byte_perm(word, 0, 0x4443);
+            row(x0, x1);
+            row(x1, x2);
+            row(x2, x3);
+            // the row after the last one of a sequence is somebody else's byte (the next sequence's, or memory that a later
+            // upload stage has not filled or validated yet): it only feeds the tensor-memory PREFETCH, whose result is then
+            // dropped, but it must never become a TMEM address outside the table -- hence the clamp to a real residue code
+            row(x3, min(__byte_perm(ahead, 0, 0x4440), static_cast<uint32_t>(kAlphabet - 1)));
+            word = ahead;
+        }
+#pragma unroll 1
+        for (uint32_t r = (!SPEC || speculate) ? len & 3u : 0u; r > 0; --r) {
+            row(word & 0xffu, min((word >> 8) & 0xffu, static_cast<uint32_t>(kAlphabet - 1)));
+            word >>= 8;
+        }
+        if constexpr (SPEC) {
+            if (!speculate || __any_sync(0xffffffffu, J >= N)) {
+                if (speculate && lane == 0 && p.speculation_failures) atomicAdd(p.speculation_failures, 1u);
+                // J may have overtaken N at some row, where B was then not N + move: scan this sequence again, exactly
+                if constexpr (TMEM_AHEAD && KT > 0) tmem_wait<KT>(te); // retire the request made by the last speculative row
+#pragma unroll
+                for (int j = 0; j < K; ++j) m[j] = NEG_INF;
+                J = NEG_INF, N = 0.0f, B = move;
+                const uint8_t* rp = p.residues + begin;
+                uint32_t x = __ldg(rp);
+                if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + x * KT, te);
+#pragma unroll 1
+                for (uint32_t i = 0; i < len; ++i) {
+                    // the byte after the last residue is another sequence's or padding: prefetch index only, clamped (see above)
+                    const uint32_t x_next = min(static_cast<uint32_t>(__ldg(rp + i + 1)), static_cast<uint32_t>(kAlphabet - 1));
+                    any_row(Exact_row{}, x, x_next);
+                    x = x_next;
+                }
+            } else {
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(J) : "f"(J));
+            }
+        }
+        } else {
         const uint32_t quads = len >> 2;
         // 4 rows (one residue word) per loop iteration, 8 or 16 where B200 sweeps showed a gain (+1..4 %, +10 % at K = 4;
         // profiles/r01/sweep_models_v6_row_unroll.jsonl, sweep_force_unroll2.txt).  It is not monotone in K -- the
@@ -579,34 +651,51 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         // passed -- the lanes' shares are combined into J, and the rest of the sequence runs with the exact row.  A hit
         // therefore costs at most one block of rows plus the slower exact rows behind it, whatever the sequence length
         // (before: the whole sequence was scanned twice, and sequences beyond 4096 rows did not speculate at all).
+#ifdef MSV_PARKED_PLAIN // development aid: let the compiler decide where the checkpoint lives
+        [[maybe_unused]] float parked[SPEC ? K + 2 : 1];
+#else
         [[maybe_unused]] volatile float parked[SPEC ? K + 2 : 1]; // volatile: really in local memory, not 46 more registers
-        uint32_t block_first = 0; // first residue word of the block at hand
-        bool overtaken = false;
-        for (;;) {
-            const uint32_t block_end = SPEC ? min(quads, block_first + kSpeculationBlockRows / 4) : quads;
+#endif
+        // (register diet: this kernel sits at its 128-register limit, and two more live values made the compiler recompute
+        // lane constants from SR_TID inside the hot loop, -5 %.  Hence: the block's first word is derived from its end --
+        // blocks start at multiples of the block size -- and the sequence index waits in shared memory.)
+        constexpr uint32_t BLOCK_WORDS = kSpeculationBlockRows / 4;
+        static_assert((BLOCK_WORDS & (BLOCK_WORDS - 1)) == 0, "block size must be a power of two");
+        const auto four_rows = [&] { // one residue word
+            const uint32_t ahead = __funnelshift_r(w1, w2, shift);
+            w1 = w2;
+            w2 = __ldg(wp);
+            ++wp;
+            const uint32_t x0 = __byte_perm(word, 0, 0x4440), x1 = __byte_perm(word, 0, 0x4441);
+            const uint32_t x2 = __byte_perm(word, 0, 0x4442), x3 = __byte_perm(word, 0, 0x4443);
+            row(x0, x1);
+            row(x1, x2);
+            row(x2, x3);
+            // the row after the last one of a sequence is somebody else's byte (the next sequence's, or memory that a later
+            // upload stage has not filled or validated yet): it only feeds the tensor-memory PREFETCH, whose result is then
+            // dropped, but it must never become a TMEM address outside the table -- hence the clamp to a real residue code
+            row(x3, min(__byte_perm(ahead, 0, 0x4440), static_cast<uint32_t>(kAlphabet - 1)));
+            word = ahead;
+        };
+        const auto park = [&] {
             if constexpr (SPEC) {
 #pragma unroll
                 for (int j = 0; j < K; ++j) parked[j] = m[j];
                 parked[K] = J;
                 parked[K + 1] = N;
             }
+        };
+        bool overtaken = false;
+        uint32_t first_row = 0; // first row of the block in which J overtook N
+        uint32_t block_end = 0; // one past the last residue word of the block at hand
+        for (;;) {
+            const uint32_t block_first = block_end;
+            block_end = SPEC ? min(quads, block_end + BLOCK_WORDS) : quads;
+            park();
+            // (written as a plain loop with `#pragma unroll`: measured 5-6 % faster than WORD_UNROLL hand-placed copies of the
+            // body with exit tests between them -- the compiler's schedule of the row body differs, variant_sweep_v2/v3.txt)
 #pragma unroll WORD_UNROLL
-            for (uint32_t i = block_first; i < block_end; ++i) {
-                const uint32_t ahead = __funnelshift_r(w1, w2, shift);
-                w1 = w2;
-                w2 = __ldg(wp);
-                ++wp;
-                const uint32_t x0 = __byte_perm(word, 0, 0x4440), x1 = __byte_perm(word, 0, 0x4441);
-                const uint32_t x2 = __byte_perm(word, 0, 0x4442), x3 = __byte_perm(word, 0, 0x4443);
-                row(x0, x1);
-                row(x1, x2);
-                row(x2, x3);
-                // the row after the last one of a sequence is somebody else's byte (the next sequence's, or memory that a later
-                // upload stage has not filled or validated yet): it only feeds the tensor-memory PREFETCH, whose result is then
-                // dropped, but it must never become a TMEM address outside the table -- hence the clamp to a real residue code
-                row(x3, min(__byte_perm(ahead, 0, 0x4440), static_cast<uint32_t>(kAlphabet - 1)));
-                word = ahead;
-            }
+            for (uint32_t i = block_first; i < block_end; ++i) four_rows();
             const bool last_block = block_end == quads;
             if (last_block) {
 #pragma unroll 1
@@ -622,10 +711,11 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
                 }
             }
             if (last_block) break;
-            block_first = block_end;
         }
+        first_row = block_end ? 4u * ((block_end - 1u) & ~(BLOCK_WORDS - 1u)) : 0u; // blocks start at multiples of their size
         if constexpr (SPEC) {
             if (overtaken) {
+                if (lane == 0 && p.speculation_failures) atomicAdd(p.speculation_failures, 1u);
                 // J overtook N inside this block, where B was then not N + move: back to the block's first row, exactly from there
                 if constexpr (TMEM_AHEAD && KT > 0) tmem_wait<KT>(te); // retire the request made by the last speculative row
 #pragma unroll
@@ -633,8 +723,9 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
                 asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(J) : "f"(parked[K])); // the lanes' shares -> J
                 N = parked[K + 1];
                 B = N + move; // J < N here: the vote before this block passed
-                const uint32_t first_row = 4u * block_first;
-                const uint8_t* rp = p.residues + begin + first_row;
+                // (the sequence's start is re-read here rather than kept in two registers through the hot loop: at the
+                // 128-register limit of this kernel that made the compiler recompute lane constants from SR_TID inside the loop)
+                const uint8_t* rp = p.residues + __ldg(p.offsets + idx) + first_row;
                 uint32_t x = first_row < len ? __ldg(rp) : 0u;
                 if constexpr (TMEM_AHEAD && KT > 0) tmem_load<KT>(tmem_lane_base + x * KT, te);
 #pragma unroll 1
@@ -648,6 +739,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
             } else {
                 asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(J) : "f"(J));
             }
+        }
         }
         if (lane == 0) store_score(p, idx, (CJ_SAME ? J : C) + move); // MSV_HMM.cpp:112
     }

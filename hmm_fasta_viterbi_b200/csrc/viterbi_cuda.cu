@@ -216,20 +216,19 @@ int msv_cuda_viterbi_model_geometry(const msv_viterbi_model* model, int* columns
     return MSV_OK;
 }
 
-int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scores_device, void* cuda_stream) {
-    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
-    if (model->device != db->device) return fail(MSV_ERR_INVALID_ARGUMENT, "model and database live on different devices");
-    if (db->n == 0) return MSV_OK;
-    if (!scores_device) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_device is NULL");
-    Device_guard guard(model->device);
-    MSV_CUDA_TRY(guard.status);
-    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+} // extern "C"
+
+// One launch over the sequences listed in `order` (n of them; `residues` = their total length, for the plan); scores land at
+// scores_device[original sequence index].
+static int viterbi_launch(msv_viterbi_model* model, msv_db* db, const uint32_t* order, size_t n, uint64_t residues, float* scores_device,
+                          cudaStream_t stream, bool likely_hits = false) {
+    {
     // Eight lanes per sequence when the model is short and every slot gets enough work to balance (it has four times more
     // slots than the warp plan; same criterion as the MSV planner: rows per slot vs the longest sequence).
     // MSV_CUDA_VITERBI_GROUPS=0 / 1 forces the choice (tuning and test aid).
     const char* forced = std::getenv("MSV_CUDA_VITERBI_GROUPS");
     const bool balanced = model->group_geo &&
-                          4 * (db->total / (static_cast<uint64_t>(model->sm_count) * (model->group_geo->threads / 8))) >=
+                          4 * (residues / (static_cast<uint64_t>(model->sm_count) * (model->group_geo->threads / 8))) >=
                               3 * std::max<uint64_t>(db->longest, 1);
     const bool grouped = model->group_geo && (forced ? forced[0] == '1' : balanced);
     const Viterbi_geometry* geo = grouped ? model->group_geo : model->geo;
@@ -237,12 +236,12 @@ int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scor
     p.table = grouped ? model->d_group_table : model->d_table;
     p.residues = db->d_residues;
     p.offsets = db->d_offsets;
-    p.order = db->d_order;
+    p.order = order;
     p.length_tr = db->d_length_tr;
     p.scores = scores_device;
     p.queue_head = db->d_queue;
     p.first_bad = db->d_first_bad;
-    p.n = static_cast<uint32_t>(db->n);
+    p.n = static_cast<uint32_t>(n);
     p.table_bytes = static_cast<uint32_t>(geo->shared_bytes());
     p.tr_B_Mk = model->tr_B_Mk;
     p.tr_E_C = model->tr_E_C;
@@ -252,17 +251,44 @@ int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scor
     // persistent CTAs, one per SM, one warp per sequence (or per four) in flight; fewer warps when there are fewer sequences
     const size_t warps_per_cta = static_cast<size_t>(geo->threads) / 32;
     const size_t per_warp = 32 / static_cast<size_t>(geo->G);
-    const size_t warps_wanted = (db->n + per_warp - 1) / per_warp;
+    const size_t warps_wanted = (n + per_warp - 1) / per_warp;
     const size_t ctas = std::max<size_t>(1, std::min<size_t>(model->sm_count, (warps_wanted + warps_per_cta - 1) / warps_per_cta));
     const size_t warps = ctas == 1 ? std::min(warps_per_cta, warps_wanted) : std::min(warps_per_cta, (warps_wanted + ctas - 1) / ctas);
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
     // speculative rows unless the database is one of long sequences, which would mostly be scanned twice
-    const bool speculate = db->total / db->n <= msv::kViterbiSpeculationMaxLength / 2 && !std::getenv("MSV_CUDA_NO_SPECULATION");
+    // ... or one of filter survivors, which are hits more often than not (their speculation would fail)
+    const bool speculate = !likely_hits && residues / n <= msv::kViterbiSpeculationMaxLength / 2 && !std::getenv("MSV_CUDA_NO_SPECULATION");
     const Scan_kernel kernel = !cj_same ? geo->fn : speculate ? geo->fn_cj_same_spec : geo->fn_cj_same;
     kernel<<<static_cast<int>(ctas), static_cast<int>(warps * 32), geo->shared_bytes(), stream>>>(p);
     msv_detail::count_launch();
     MSV_CUDA_TRY(cudaGetLastError());
     return MSV_OK;
+    }
+}
+
+extern "C" {
+
+int msv_cuda_db_viterbi_device(msv_viterbi_model* model, msv_db* db, float* scores_device, void* cuda_stream) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (model->device != db->device) return fail(MSV_ERR_INVALID_ARGUMENT, "model and database live on different devices");
+    if (db->n == 0) return MSV_OK;
+    if (!scores_device) return fail(MSV_ERR_INVALID_ARGUMENT, "scores_device is NULL");
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    return viterbi_launch(model, db, db->d_order, db->n, db->total, scores_device, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int msv_cuda_db_viterbi_subset_device(msv_viterbi_model* model, msv_db* db, const uint32_t* indices_device, size_t count, float* scores_device,
+                                      void* cuda_stream) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    if (model->device != db->device) return fail(MSV_ERR_INVALID_ARGUMENT, "model and database live on different devices");
+    if (count == 0) return MSV_OK;
+    if (count > db->n || !indices_device || !scores_device) return fail(MSV_ERR_INVALID_ARGUMENT, "bad subset");
+    Device_guard guard(model->device);
+    MSV_CUDA_TRY(guard.status);
+    // (the subset's own residue count is not known on the host: the database's mean length stands in for the plan)
+    const uint64_t residues = std::max<uint64_t>(1, db->total / db->n) * count;
+    return viterbi_launch(model, db, indices_device, count, residues, scores_device, static_cast<cudaStream_t>(cuda_stream), true);
 }
 
 int msv_cuda_db_viterbi(msv_viterbi_model* model, msv_db* db, float* scores_host) {

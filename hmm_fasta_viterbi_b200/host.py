@@ -81,6 +81,8 @@ lib.msvh_viterbi_parallel_run_on_packed.argtypes = [_vp, _vp, _f32]
 lib.msvh_viterbi_parallel_run_on_device_database.argtypes = [_vp, _vp, _f32]
 lib.msvh_viterbi_filter.restype = C.c_long
 lib.msvh_viterbi_filter.argtypes = [_vp, _vp, C.c_float, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.msvh_viterbi_filter_survivors.restype = C.c_long
+lib.msvh_viterbi_filter_survivors.argtypes = [_vp, _vp, C.c_float, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 lib.msvh_msv_filter.restype = C.c_long
 lib.msvh_msv_filter.argtypes = [_vp, _vp, C.c_float, C.c_size_t, _vp, _vp, _vp, _vp]
 lib.msvh_msv_parallel_run_on_packed_devices.argtypes = [_vp, _vp, C.POINTER(C.c_int), C.c_int, C.c_int, _f32]
@@ -305,6 +307,18 @@ class Viterbi_HMM:
         score, bits, p = (np.empty(max(cap, 1), np.float32) for _ in range(3))
         found = lib.msvh_viterbi_filter(self._h, database._h, float(threshold), cap, index.ctypes.data, score.ctypes.data,
                                         bits.ctypes.data, p.ctypes.data)
+        if found < 0:
+            _raise(int(found))
+        return {"index": index[:found], "score": score[:found], "bits": bits[:found], "p_value": p[:found]}
+
+    def viterbi_filter_survivors(self, database: Device_database, threshold: float = 1e-3) -> dict:
+        """The Viterbi filter over the survivors of the last MSV_HMM.msv_filter on this database (their index list stayed on
+        the GPU): index/score/bits/p_value of the sequences that also pass this stage."""
+        cap = len(database)
+        index = np.empty(max(cap, 1), np.uint64)
+        score, bits, p = (np.empty(max(cap, 1), np.float32) for _ in range(3))
+        found = lib.msvh_viterbi_filter_survivors(self._h, database._h, float(threshold), cap, index.ctypes.data, score.ctypes.data,
+                                                  bits.ctypes.data, p.ctypes.data)
         if found < 0:
             _raise(int(found))
         return {"index": index[:found], "score": score[:found], "bits": bits[:found], "p_value": p[:found]}

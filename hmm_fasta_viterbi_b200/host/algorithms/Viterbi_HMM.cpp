@@ -1,5 +1,6 @@
 #include "Viterbi_HMM.hpp"
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 
@@ -88,4 +89,24 @@ std::vector<MSV_hit> Viterbi_HMM::viterbi_filter(const Device_database& database
     for (size_t q = 0; q < n; ++q)
         if (p_values[q] <= threshold) hits.push_back(MSV_hit{q, scores[q], bits[q], p_values[q]});
     return hits;
+}
+
+std::vector<MSV_hit> Viterbi_HMM::viterbi_filter_survivors(const Device_database& database, float threshold) {
+    if (database.device() != device_index) set_device(database.device());
+    auto capacity = std::max<size_t>(1024, database.size() / 64);
+    for (;;) {
+        auto index = std::vector<uint32_t>(capacity);
+        auto scores = std::vector<float>(capacity), bits = std::vector<float>(capacity), p_values = std::vector<float>(capacity);
+        auto found = size_t(0);
+        const auto status = msv_cuda_db_viterbi_filter_survivors(on_device(), database.handle(), mu, lambda, threshold, index.data(), scores.data(),
+                                                                 bits.data(), p_values.data(), capacity, &found);
+        if (status != MSV_OK) throw_viterbi_error("Viterbi_HMM::viterbi_filter_survivors", status);
+        if (found > capacity) { // (the survivors list is untouched by this stage, so the call can simply be repeated)
+            capacity = found;
+            continue;
+        }
+        auto hits = std::vector<MSV_hit>(found);
+        for (size_t i = 0; i < found; ++i) hits[i] = MSV_hit{index[i], scores[i], bits[i], p_values[i]};
+        return hits;
+    }
 }

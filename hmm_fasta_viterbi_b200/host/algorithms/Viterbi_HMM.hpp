@@ -33,6 +33,9 @@ class Viterbi_HMM {
     // The Viterbi *filter*, second stage of HMMER3's pipeline: scan, bit scores and Gumbel P-values (STATS LOCAL VITERBI) on
     // the device; keeps sequences with P <= threshold (HMMER3's default F2 is 1e-3).  Hits reuse MSV_hit.
     std::vector<MSV_hit> viterbi_filter(const Device_database& database, float threshold = 1e-3f);
+    // The same restricted to the SURVIVORS of the last MSV_HMM::msv_filter on this database -- HMMER3's pipeline order.  The
+    // survivors' index list never left the GPU: the scan reads the resident database through it, nothing is re-packed.
+    std::vector<MSV_hit> viterbi_filter_survivors(const Device_database& database, float threshold = 1e-3f);
 
     size_t length() const { return model_length; } // LENG + 1
     int device() const { return device_index; }

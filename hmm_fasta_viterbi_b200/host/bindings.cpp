@@ -200,6 +200,20 @@ long msvh_viterbi_filter(void* m, void* d, float threshold, size_t capacity, uin
     });
     return status == 0 ? found : status;
 }
+long msvh_viterbi_filter_survivors(void* m, void* d, float threshold, size_t capacity, uint64_t* index, float* score, float* bits, float* p) {
+    long found = -1;
+    const int status = guarded([&] {
+        const auto hits = static_cast<Viterbi_HMM*>(m)->viterbi_filter_survivors(*static_cast<Device_database*>(d), threshold);
+        found = static_cast<long>(hits.size());
+        for (size_t i = 0; i < hits.size() && i < capacity; ++i) {
+            index[i] = hits[i].sequence;
+            score[i] = hits[i].score;
+            bits[i] = hits[i].bits;
+            p[i] = hits[i].p_value;
+        }
+    });
+    return status == 0 ? found : status;
+}
 int msvh_viterbi_parallel_run_on_device_database(void* m, void* d, float* scores) {
     return guarded([&] {
         const auto got = static_cast<Viterbi_HMM*>(m)->parallel_run_on_sequences(*static_cast<Device_database*>(d));

@@ -203,6 +203,19 @@ int msv_cuda_db_filter_device(msv_db* db, const float* scores_device, float mu, 
 int msv_cuda_db_score_filter(msv_model* model, msv_db* db, float mu, float lambda, float* scores_host, float* bits_host,
                              float* pvalues_host);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * The filter stages kept ON THE DEVICE (HMMER3's acceleration pipeline: MSV filter, P <= F1 = 0.02, then the Viterbi filter
+ * on the survivors, P <= F2 = 1e-3).  One synchronous call per stage; only the HITS cross PCIe:
+ *   msv_cuda_db_msv_filter                 scan + statistics + selection (stream compaction in database order) of the
+ *                                          sequences with P <= threshold; their indices stay on the device as "survivors";
+ *   msv_cuda_db_viterbi_filter_survivors   Viterbi scan of exactly those survivors (the resident database is read through
+ *                                          the index list, nothing is re-packed), statistics, second selection.
+ * The hit arrays have room for `capacity` entries each (any may be NULL); *n_hits is the number selected (it may exceed
+ * `capacity`: then the first `capacity` are returned).  hit_index is the sequence's index in the database.
+ * ------------------------------------------------------------------------------------------------------------- */
+int msv_cuda_db_msv_filter(msv_model* model, msv_db* db, float mu, float lambda, float threshold, uint32_t* hit_index, float* hit_score,
+                           float* hit_bits, float* hit_pvalue, size_t capacity, size_t* n_hits);
+
 /* Page-lock (pin) a caller-owned host buffer so that uploads from it run at full PCIe / C2C speed and overlap with the
  * scan (msv_cuda_score_batch, msv_cuda_db_create take any host memory; pageable memory is staged by the driver at a
  * fraction of the link speed).  Registration is expensive (of the order of 1 ms per 4 MB): do it once per database. */
@@ -244,6 +257,13 @@ int msv_cuda_db_viterbi(msv_viterbi_model* model, msv_db* db, float* scores_host
  * msv_cuda_db_filter_device); n floats per host array, bits_host / pvalues_host may be NULL. */
 int msv_cuda_db_viterbi_filter(msv_viterbi_model* model, msv_db* db, float mu, float lambda, float* scores_host, float* bits_host,
                                float* pvalues_host);
+/* a SUBSET of a resident database, given as `count` sequence indices in device memory (e.g. the survivors of a filter
+ * stage); scores_device is indexed by the ORIGINAL sequence index (n floats); asynchronous on `cuda_stream`. */
+int msv_cuda_db_viterbi_subset_device(msv_viterbi_model* model, msv_db* db, const uint32_t* indices_device, size_t count, float* scores_device,
+                                      void* cuda_stream);
+/* second filter stage: see msv_cuda_db_msv_filter */
+int msv_cuda_db_viterbi_filter_survivors(msv_viterbi_model* model, msv_db* db, float mu, float lambda, float threshold, uint32_t* hit_index,
+                                         float* hit_score, float* hit_bits, float* hit_pvalue, size_t capacity, size_t* n_hits);
 /* HOST buffers in and out: upload + bucket + scan + download in one synchronous call. */
 int msv_cuda_viterbi_batch(msv_viterbi_model* model, const uint8_t* residues, const uint64_t* offsets, size_t n, float* scores_host);
 

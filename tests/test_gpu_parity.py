@@ -790,3 +790,65 @@ def test_single_sequence_wavefront_kernel_long_models(oracle):
         for n in (0, 5, 333, 2000):
             s = rng.integers(0, 20, size=n, dtype=np.uint8)
             assert bits(model.score_sequence(s)) == bits(oracle.score_codes(table, tr3, s)), (leng, n)
+
+
+# ---- filter stages kept on the device (csrc/filter_cuda.cu) -------------------------------------------------------------
+def test_filter_pipeline_selects_on_the_device(oracle):
+    """MSV filter -> Viterbi filter on the survivors, HMMER3's pipeline order, with the selection and the survivors' index list
+    on the GPU: the hits of both stages must be exactly those a host-side selection over the full per-sequence arrays gives,
+    in database order, with the same numbers; a capacity that is too small truncates and still reports the true count."""
+    import ctypes as C
+    name = "400.hmm"
+    prof = msv.Profile_HMM(hmm_path(name))
+    rng = np.random.default_rng(23)
+    cons = prof.match_emissions[1:].argmax(axis=1).astype(np.uint8)
+    seqs = [rng.integers(0, 20, size=int(k), dtype=np.uint8) for k in rng.integers(50, 700, size=30_000)]
+    for q in rng.choice(len(seqs), size=300, replace=False):  # homologs of varying strength, scattered over the database
+        a = int(rng.integers(0, 200))
+        seg = cons[a:a + int(rng.integers(30, 200))].copy()
+        seg[rng.random(seg.size) < rng.uniform(0.0, 0.5)] = rng.integers(0, 20)
+        seqs[q] = np.concatenate([seqs[q][:30], seg, seqs[q][30:]])
+    packed = msv.Packed_sequences.from_arrays(*pack(seqs))
+    database = msv.Device_database(packed)
+    msv_model, vit_model = msv.MSV_HMM(prof), msv.Viterbi_HMM(prof)
+
+    # reference selection on the host from the full arrays (the round-1 route)
+    raw = msv_model.parallel_run_on_sequences(database)
+    h = oracle.load_hmm(hmm_path(name))
+    dev_model = msv.Model(_cabi.emission_table(h["match_emissions"]), *_cabi.model_transitions(h["model_length"]))
+    db = msv.Database(packed.residues, packed.offsets)
+    import torch
+    scores = torch.from_numpy(raw.copy()).cuda()
+    bits_d, p_d = torch.empty_like(scores), torch.empty_like(scores)
+    db.filter_device(scores, float(prof.stats_local_msv_mu), float(prof.stats_local_msv_lambda), bits_d, p_d)
+    torch.cuda.synchronize()
+    p_all, bits_all = p_d.cpu().numpy(), bits_d.cpu().numpy()
+    want_stage1 = np.flatnonzero(p_all <= np.float32(0.02))
+
+    hits = msv_model.msv_filter(database, 0.02)
+    assert hits["index"].astype(np.int64).tolist() == want_stage1.tolist() and len(want_stage1) > 300
+    assert ubits(hits["score"]).tolist() == ubits(raw[want_stage1]).tolist()
+    assert ubits(hits["bits"]).tolist() == ubits(bits_all[want_stage1]).tolist()
+    assert ubits(hits["p_value"]).tolist() == ubits(p_all[want_stage1]).tolist()
+
+    # second stage over the survivors only
+    vit_all = vit_model.parallel_run_on_sequences(database)
+    full = vit_model.viterbi_filter(database, 1e-3)  # statistics of every sequence, selected on the host
+    want_stage2 = [int(i) for i in full["index"] if int(i) in set(want_stage1.tolist())]
+    survivors = vit_model.viterbi_filter_survivors(database, 1e-3)
+    assert survivors["index"].astype(np.int64).tolist() == want_stage2 and 100 < len(want_stage2) < len(want_stage1)
+    assert ubits(survivors["score"]).tolist() == ubits(vit_all[np.array(want_stage2)]).tolist()
+    lookup = {int(i): k for k, i in enumerate(full["index"])}
+    rows = [lookup[i] for i in want_stage2]
+    assert ubits(survivors["p_value"]).tolist() == ubits(full["p_value"][rows]).tolist()
+
+    # raw C entry point: small capacity
+    idx = np.zeros(5, np.uint32)
+    sc, bt, pv = (np.zeros(5, np.float32) for _ in range(3))
+    found = C.c_size_t()
+    _cabi.check(_cabi.lib.msv_cuda_db_msv_filter(dev_model.handle, db.handle, float(prof.stats_local_msv_mu), float(prof.stats_local_msv_lambda),
+                                                 0.02, idx.ctypes.data, sc.ctypes.data, bt.ctypes.data, pv.ctypes.data, 5, C.byref(found)))
+    assert found.value == len(want_stage1) and idx.tolist() == want_stage1[:5].tolist()
+    # a database nobody passes
+    none = msv_model.msv_filter(database, -1.0)
+    assert len(none["index"]) == 0 and len(vit_model.viterbi_filter_survivors(database, 1e-3)["index"]) == 0
