@@ -26,7 +26,7 @@ DECLARED_SYMBOLS = (
     "msv_cuda_abi_version", "msv_cuda_last_error", "msv_cuda_device_count",
     "msv_host_emission_table", "msv_host_model_transitions", "msv_host_length_transitions", "msv_host_encode",
     "msv_host_partition_by_cells",
-    "msv_cuda_model_create", "msv_cuda_model_destroy", "msv_cuda_model_geometry", "msv_cuda_model_plan",
+    "msv_cuda_model_create", "msv_cuda_model_destroy", "msv_cuda_model_geometry", "msv_cuda_model_plan", "msv_cuda_model_speculation",
     "msv_cuda_db_create", "msv_cuda_db_destroy", "msv_cuda_db_info",
     "msv_cuda_db_score_device", "msv_cuda_db_score_gather", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
     "msv_cuda_db_filter_device", "msv_cuda_db_score_filter", "msv_cuda_host_register", "msv_cuda_host_unregister",
@@ -74,6 +74,7 @@ lib.msv_cuda_model_destroy.argtypes = [C.c_void_p]
 lib.msv_cuda_model_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                         C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
 lib.msv_cuda_model_plan.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+lib.msv_cuda_model_speculation.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_int)]
 lib.msv_cuda_db_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
 lib.msv_cuda_db_destroy.argtypes = [C.c_void_p]
 lib.msv_cuda_db_info.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -247,6 +248,13 @@ class Model:
         k, w, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         check(lib.msv_cuda_model_wave_geometry(self.handle, C.byref(k), C.byref(w), C.byref(c), C.byref(d)))
         return {"columns_per_lane": k.value, "warps": w.value, "ctas": c.value, "diagonal_ctas": d.value}
+
+    @property
+    def speculation(self) -> dict:
+        """Running totals behind the choice of the speculating kernel (see msv_cuda.h) and what the next scan would use."""
+        f, o, b = C.c_uint(), C.c_uint(), C.c_int()
+        check(lib.msv_cuda_model_speculation(self.handle, C.byref(f), C.byref(o), C.byref(b)))
+        return {"failed": f.value, "offered": o.value, "blocks_next": bool(b.value)}
 
     def plan(self, database: "Database") -> dict:
         """Launch plan a scan of `database` would use: kernel family (lanes per sequence) and sequences per CTA."""

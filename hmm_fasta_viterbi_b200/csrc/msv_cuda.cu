@@ -54,6 +54,7 @@ struct Geometry {
     Scan_kernel fn_cj_same; // tr_E_C == tr_E_J bitwise (C is J); same as fn for the generic family
     int variant = 0;        // 0: tensor-memory columns are each lane's lowest; 1: TMEM_AHEAD (they are the highest, loaded a row ahead)
     Scan_kernel fn_cj_same_exact = nullptr; // warp family: when fn_cj_same speculates B = N + move (and verifies), the kernel that never does
+    Scan_kernel fn_cj_same_blocks = nullptr; // warp family: speculation in checkpointed blocks (fn_cj_same speculates on whole sequences)
     Scan_kernel fn_group_spec = nullptr;    // lane-group family (G = 8): speculative scan; failures go to a second, exact launch
     // (four lanes per sequence: two interleaved copies of the table, see msv_scan_kernel)
     size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET) * (K - std::max(KT, 0)) * std::max(G, KT < 0 ? 8 : G) * sizeof(float); }
@@ -67,7 +68,7 @@ template <int G, int K> constexpr Scan_kernel group_spec_kernel() {
 }
 template <int G, int K> constexpr Geometry generic_entry() {
     return Geometry{G, K, -1, threads_for(K), msv::msv_scan_kernel<G, K, threads_for(K), false>,
-                    msv::msv_scan_kernel<G, K, threads_for(K), true>, 0, nullptr, group_spec_kernel<G, K>()};
+                    msv::msv_scan_kernel<G, K, threads_for(K), true>, 0, nullptr, nullptr, group_spec_kernel<G, K>()};
 }
 // Speculative rows (B = N + move, verified per sequence; msv_kernels.cuh) are instantiated where B200 sweeps showed them
 // ahead of the exact rows (profiles/r01/sweep_speculation*.txt: +13 % at K = 4, +2..6 % at K = 16..22 and 32..38, level at
@@ -75,8 +76,12 @@ template <int G, int K> constexpr Geometry generic_entry() {
 // the instruction cache).
 constexpr bool speculation_pays(int K) { return K <= 44 && !(K >= 26 && K <= 30); }
 template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_kernel() {
-    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD, true>;
+    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD, 1>;
     else return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD>;
+}
+template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_blocks_kernel() {
+    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD, 2>;
+    else return nullptr;
 }
 template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_exact_kernel() {
     if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD>;
@@ -84,7 +89,8 @@ template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_exact_
 }
 template <int K, int KT> constexpr Geometry warp_entry() {
     return Geometry{32, K, KT, warp_threads_for(K, KT), msv::msv_scan_warp_kernel<K, KT, warp_threads_for(K, KT), false>,
-                    cj_same_kernel<K, KT, warp_threads_for(K, KT), false>(), 0, cj_same_exact_kernel<K, KT, warp_threads_for(K, KT), false>()};
+                    cj_same_kernel<K, KT, warp_threads_for(K, KT), false>(), 0, cj_same_exact_kernel<K, KT, warp_threads_for(K, KT), false>(),
+                    cj_same_blocks_kernel<K, KT, warp_threads_for(K, KT), false>()};
 }
 
 constexpr int quad_threads_for(int K) { return K <= 12 ? 1024 : K <= 28 ? 768 : 512; }
@@ -94,12 +100,12 @@ template <int K, int KT> constexpr Geometry quad_entry() { // four warps (128 la
 }
 template <int K, int KT, int T> constexpr Geometry warp_entry_threads() {
     return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false>, cj_same_kernel<K, KT, T, false>(), 0,
-                    cj_same_exact_kernel<K, KT, T, false>()};
+                    cj_same_exact_kernel<K, KT, T, false>(), cj_same_blocks_kernel<K, KT, T, false>()};
 }
 
 template <int K, int KT, int T> constexpr Geometry warp_entry_ahead() {
     return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false, true>, cj_same_kernel<K, KT, T, true>(), 1,
-                    cj_same_exact_kernel<K, KT, T, true>()};
+                    cj_same_exact_kernel<K, KT, T, true>(), cj_same_blocks_kernel<K, KT, T, true>()};
 }
 
 #define MSV_FOR_EACH_K(X, A)                                                                                           \
@@ -263,6 +269,13 @@ struct msv_model {
     float tr_B_Mk = 0, tr_E_C = 0, tr_E_J = 0;
     int sm_count = 0;
     msv_db* workspace = nullptr; // reused by msv_cuda_score_batch / msv_cuda_score_sequence
+    // Feedback for the choice between the two speculating warp kernels (launch_scan): running totals on the device
+    // ([0] failed speculations, [1] sequences offered), copied after every such launch into pinned host memory, which the
+    // next launch reads without waiting -- a heuristic input, so a stale value is fine.
+    unsigned int* d_speculation_totals = nullptr;
+    volatile unsigned int* h_speculation_totals = nullptr;
+    unsigned int seen_failures = 0, seen_offered = 0; // totals at the last decision that had enough new sequences behind it
+    bool hits_are_common = false;
     // single-sequence latency path (msv_wave_kernels.cuh): a chain of warps over a thread-block cluster; built when
     // tr_E_C == tr_E_J (the kernel speculates B = N + move) and the chain fits a cluster
     struct Wave {
@@ -617,11 +630,36 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
         return MSV_OK;
     }
     Scan_kernel kernel = cj_same ? geo->fn_cj_same : geo->fn;
-    // (the speculative rows checkpoint every 64 rows, so a hit costs one block whatever the sequence length: no length limit)
-    if (cj_same && geo->fn_cj_same_exact && std::getenv("MSV_CUDA_NO_SPECULATION")) kernel = geo->fn_cj_same_exact;
+    // Two speculating warp kernels (msv_kernels.cuh).  fn_cj_same speculates on a whole sequence (up to 4096 rows) and scans
+    // it again when the vote at its end fails: the faster loop (10.08 vs 9.85 TCUPS at 1400 columns), a whole extra pass per
+    // hit.  fn_cj_same_blocks checkpoints every 64 rows: a hit costs one block whatever the sequence length.  Break-even is
+    // near 2 % of the sequences failing (1 + 1.4 f = 1.023 + 0.25 f), so: blocks for long sequences (they would not
+    // speculate at all otherwise) and when the previous scans with this model saw hits that often.
+    // MSV_CUDA_SPECULATION=whole|blocks|none overrides (tuning aid; MSV_CUDA_NO_SPECULATION is the older spelling of none).
+    bool feedback = false;
+    if (cj_same && geo->fn_cj_same_exact) {
+        const char* env = std::getenv("MSV_CUDA_SPECULATION");
+        const std::string forced_mode = std::getenv("MSV_CUDA_NO_SPECULATION") ? "none" : env ? env : "";
+        if (model->h_speculation_totals && &plan == &model->bulk) {
+            feedback = true;
+            const unsigned int failures = model->h_speculation_totals[0], offered = model->h_speculation_totals[1];
+            if (offered - model->seen_offered >= 4096u) { // unsigned differences: the totals may wrap
+                model->hits_are_common = 50ull * (failures - model->seen_failures) > (offered - model->seen_offered);
+                model->seen_failures = failures;
+                model->seen_offered = offered;
+            }
+        }
+        const bool long_sequences = residues / count > 1024;
+        if (forced_mode == "none") kernel = geo->fn_cj_same_exact, feedback = false;
+        else if (forced_mode == "blocks" || (forced_mode != "whole" && (long_sequences || model->hits_are_common))) kernel = geo->fn_cj_same_blocks;
+    }
+    if (feedback) p.speculation_failures = model->d_speculation_totals;
     kernel<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
     ++g_launches;
     MSV_CUDA_TRY(cudaGetLastError());
+    if (feedback)
+        MSV_CUDA_TRY(cudaMemcpyAsync(const_cast<unsigned int*>(model->h_speculation_totals), model->d_speculation_totals,
+                                     2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
     return MSV_OK;
 }
 
@@ -1052,7 +1090,7 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         if (static_cast<size_t>(prop.sharedMemPerBlockOptin) < plan.shared_bytes + 1024) return cudaErrorInvalidConfiguration;
         cudaError_t err = cudaMalloc(&plan.d_table, plan.table_bytes);
         if (err == cudaSuccess) err = cudaMemcpy(plan.d_table, laid.data(), plan.table_bytes, cudaMemcpyHostToDevice);
-        for (Scan_kernel fn : {geo->fn, geo->fn_cj_same, geo->fn_cj_same_exact, geo->fn_group_spec})
+        for (Scan_kernel fn : {geo->fn, geo->fn_cj_same, geo->fn_cj_same_exact, geo->fn_cj_same_blocks, geo->fn_group_spec})
             if (err == cudaSuccess && fn)
                 err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(plan.shared_bytes));
@@ -1081,6 +1119,19 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
             return fail(MSV_ERR_MODEL_TOO_LONG, "emission table of a %zu-column model exceeds shared + tensor memory", columns);
         return fail(MSV_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(err));
     }
+    if (model->bulk.geo && model->bulk.geo->fn_cj_same_blocks) { // optional: without it the whole-sequence mode stays
+        void* pinned = nullptr;
+        if (cudaMalloc(&model->d_speculation_totals, 2 * sizeof(unsigned int)) == cudaSuccess &&
+            cudaMemset(model->d_speculation_totals, 0, 2 * sizeof(unsigned int)) == cudaSuccess &&
+            cudaHostAlloc(&pinned, 2 * sizeof(unsigned int), cudaHostAllocPortable) == cudaSuccess) {
+            model->h_speculation_totals = static_cast<volatile unsigned int*>(pinned);
+            model->h_speculation_totals[0] = model->h_speculation_totals[1] = 0;
+        } else {
+            cudaFree(model->d_speculation_totals);
+            model->d_speculation_totals = nullptr;
+            (void)cudaGetLastError();
+        }
+    }
     // the single-sequence latency plan is optional: any failure here just leaves the four-warp kernel in charge
     if (std::memcmp(&tr_E_C, &tr_E_J, sizeof(float)) == 0 && !forced && !std::getenv("MSV_CUDA_NO_WAVE")) {
         if (wave_build(model, emission_scores, columns) != cudaSuccess) {
@@ -1098,6 +1149,8 @@ int msv_cuda_model_destroy(msv_model* model) {
     {
         Device_guard guard(model->device);
         wave_release(model);
+        cudaFree(model->d_speculation_totals);
+        if (model->h_speculation_totals) cudaFreeHost(const_cast<unsigned int*>(model->h_speculation_totals));
         cudaFree(model->bulk.d_table);
         cudaFree(model->octet.d_table);
         cudaFree(model->narrow.d_table);
@@ -1125,6 +1178,17 @@ int msv_cuda_model_wave_geometry(const msv_model* model, int* columns_per_lane, 
     if (warps) *warps = static_cast<int>(model->wave.warps);
     if (ctas) *ctas = static_cast<int>(model->wave.ctas);
     if (diagonal_ctas) *diagonal_ctas = model->wave.d_diag_table ? static_cast<int>(model->wave.diag_ctas) : 0;
+    return MSV_OK;
+}
+
+int msv_cuda_model_speculation(const msv_model* model, unsigned int* failed, unsigned int* offered, int* blocks_next) {
+    if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
+    const unsigned int f = model->h_speculation_totals ? model->h_speculation_totals[0] : 0u;
+    const unsigned int o = model->h_speculation_totals ? model->h_speculation_totals[1] : 0u;
+    if (failed) *failed = f;
+    if (offered) *offered = o;
+    if (blocks_next) // the decision launch_scan would take now (it also folds the totals in once 4096 new sequences are behind them)
+        *blocks_next = (o - model->seen_offered >= 4096u) ? 50ull * (f - model->seen_failures) > (o - model->seen_offered) : model->hits_are_common;
     return MSV_OK;
 }
 

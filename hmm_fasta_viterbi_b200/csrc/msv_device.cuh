@@ -32,7 +32,8 @@ struct Scan_params {
     uint32_t* redo_list;
     unsigned int* redo_count;
     const unsigned int* n_device;
-    // sequences whose speculation failed in this scan (statistics for the host's choice of the speculation mode); may be NULL
+    // running totals for the host's choice of the speculation mode (may be NULL): [0] sequences whose speculation failed,
+    // [1] sequences offered to a speculating warp kernel
     unsigned int* speculation_failures;
 };
 

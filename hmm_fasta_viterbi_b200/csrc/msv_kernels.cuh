@@ -437,6 +437,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
 
     // never index the table with an unvalidated residue code: the validation kernel precedes this launch on the stream
     if (p.first_bad != nullptr && *p.first_bad != ~0ull) return;
+    if constexpr (SPEC) // [1] counts the sequences offered to speculation, [0] the failures among them (below)
+        if (blockIdx.x == 0 && threadIdx.x == 0 && p.speculation_failures) atomicAdd(p.speculation_failures + 1, p.n);
 
     // ---- stage the shared-memory part with the TMA unit ----
     if (threadIdx.x == 0) mbarrier_init(&table_ready, 1);

@@ -663,7 +663,7 @@ def test_speculation_falls_back_exactly_on_hits(oracle, name, monkeypatch):
     consensus = np.argmax(h["match_emissions"][1:], axis=1).astype(np.uint8)
     rng = np.random.default_rng(leng)
     seqs = []
-    for q in range(1500):
+    for q in range(6000):  # enough sequences for the launch planner to take the warp-per-sequence (or lane-group) plan
         kind = q % 5
         if kind == 0:
             seqs.append(rng.integers(0, 20, size=int(rng.integers(0, 400)), dtype=np.uint8))
@@ -693,9 +693,29 @@ def test_speculation_falls_back_exactly_on_hits(oracle, name, monkeypatch):
     monkeypatch.setenv("MSV_CUDA_NO_SPECULATION", "1")
     assert ubits(db.score(model)).tolist() == ubits(want).tolist()
     monkeypatch.delenv("MSV_CUDA_NO_SPECULATION")
-    # a database of long sequences only (mean length above the launch-level threshold) takes the exact kernel
+    # both speculating kernels (whole sequences / checkpointed blocks of 64 rows) and the one that never speculates
+    for mode in ("whole", "blocks", "none"):
+        monkeypatch.setenv("MSV_CUDA_SPECULATION", mode)
+        assert ubits(db.score(model)).tolist() == ubits(want).tolist(), mode
+        assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist(), mode
+    monkeypatch.delenv("MSV_CUDA_SPECULATION")
+    # a database of long sequences only (mean length above the launch-level threshold) takes the block-wise kernel
     long_codes, long_offsets = pack(seqs[-12:])
     assert ubits(model.score_batch(long_codes, long_offsets)).tolist() == ubits(want[-12:]).tolist()
+    # feedback: after enough sequences of this hit-rich database the library switches to blocks by itself ...
+    if model.plan(db)["lanes_per_sequence"] == 32 and model.geometry["columns_per_lane"] <= 44:
+        for _ in range(3):
+            assert ubits(db.score(model)).tolist() == ubits(want).tolist()
+        state = model.speculation
+        assert state["offered"] >= 4096 and state["failed"] > state["offered"] // 4 and state["blocks_next"], state
+        # ... and back to whole sequences on a database without hits
+        noise = [rng.integers(0, 20, size=int(rng.integers(50, 400)), dtype=np.uint8) for _ in range(5000)]
+        noise_codes, noise_offsets = pack(noise)
+        noise_want = oracle.score_batch(table, tr3, noise_codes, noise_offsets, threads=CORES)
+        noise_db = msv.Database(noise_codes, noise_offsets)
+        for _ in range(3):
+            assert ubits(noise_db.score(model)).tolist() == ubits(noise_want).tolist()
+        assert not model.speculation["blocks_next"], model.speculation
 
 
 @pytest.mark.parametrize("name,geometry", [("100.hmm", "8,16"), ("200.hmm", "8,28"), ("100.hmm", "4,28"), ("200.hmm", "4,52")])
