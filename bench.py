@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--no-peer-gather", action="store_true", help="N > 1: gather the scores with NCCL instead of the fused peer-memory stores")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the side measurements (configs 2, 3, 5, hit-rate sweep, FASTA)")
     ap.add_argument("--no-side-keys", action="store_true", help="N > 1: skip weak_scaling / nccl_gather / single_process_multi_gpu")
+    ap.add_argument("--single-process-child", default=None, help=argparse.SUPPRESS)  # internal: see single_process_before_ranks
     return ap.parse_args()
 
 
@@ -463,11 +464,91 @@ def viterbi_side_line(torch, msv, _cabi, resident, database, device: int) -> dic
 
 
 # ---- our arm ----------------------------------------------------------------------------------------------------------
+def single_process_child(args) -> None:
+    """One process, all GPUs, through the C ABI (msv_cuda_multi_score_batch): the whole job's database in pinned host memory
+    in, the whole job's scores in one host buffer out.  No torch, no NCCL process group; prints one JSON object."""
+    import hmm_fasta_viterbi_b200 as msv
+    from hmm_fasta_viterbi_b200 import _cabi
+
+    ngpu = min(args.gpus, _cabi.device_count())
+    profile = msv.Profile_HMM(os.path.join(REPO, "fixtures", "profile_HMMs", args.model))
+    packed = msv.Packed_sequences.synthetic_swissprot_like(args.sequences, SEED)
+    codes, offsets = np.ascontiguousarray(packed.residues), np.ascontiguousarray(packed.offsets)
+    out = np.empty(len(offsets) - 1, np.float32)
+    for a in (codes, offsets, out):  # page-locked, as the e2e legs of the ranks use
+        _cabi.check(_cabi.lib.msv_cuda_host_register(a.ctypes.data, a.nbytes))
+    cells = float(offsets[-1]) * (profile.model_length - 1)
+    models = [msv.Model(_cabi.emission_table(profile.match_emissions), *_cabi.model_transitions(profile.model_length), device=g)
+              for g in range(ngpu)]
+    multi = _cabi.MultiGpu(models)
+    report, kept = {"gpus": ngpu}, None
+    for name, mode in (("host", _cabi.GATHER_HOST), ("peer", _cabi.GATHER_PEER), ("nccl", _cabi.GATHER_NCCL)):
+        try:
+            for _ in range(3):
+                multi.score_batch(codes, offsets, out, gather=mode)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                multi.score_batch(codes, offsets, out, gather=mode)
+            dt = (time.perf_counter() - t0) / args.steps
+            report[name] = {"e2e_gcups": round(cells / dt / 1e9, 1), "ms_per_step": round(dt * 1e3, 3)}
+            if kept is None:
+                kept = out.copy()
+            else:
+                report[name]["same_bits_as_first_mode"] = bool((kept.view(np.uint32) == out.view(np.uint32)).all())
+        except Exception as e:  # noqa: BLE001
+            report[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if kept is not None:
+        np.save(args.single_process_child, kept)
+        report["scores_file"] = args.single_process_child
+    report["api"] = ("msv_cuda_multi_score_batch: one process, one host thread per GPU, pinned host database in, host scores out; "
+                     "measured in a process of its own before the ranks created their CUDA contexts (a GPU shared by two "
+                     "processes time-slices, which is not what a user of the single-process API has)")
+    print(json.dumps(report))
+
+
+def single_process_before_ranks(args, rank: int, world: int):
+    """N > 1: rank 0 runs single_process_child in a child process while the other ranks wait on the rendezvous store, before
+    any rank has touched CUDA.  (Measured from rank 0 itself after the main loop, the same call took 66 ms instead of 26 ms at
+    N = 2 -- profiles/r02/bench_b_n2_strong.json vs multi_probe_v1.json: every other GPU then also holds another rank's
+    context.)"""
+    import subprocess
+    import tempfile
+    from datetime import timedelta
+
+    import torch.distributed as dist
+
+    if os.environ.get("TORCHELASTIC_USE_AGENT_STORE") != "True":  # not under torchrun: no store to wait on before the process group
+        return None
+    store = dist.TCPStore(os.environ["MASTER_ADDR"], int(os.environ["MASTER_PORT"]), world, False, timedelta(seconds=900))
+    result = None
+    if rank == 0:
+        scores_file = os.path.join(tempfile.gettempdir(), f"msv_single_process_{os.getpid()}.npy")
+        try:
+            done = subprocess.run([sys.executable, os.path.abspath(__file__), "--gpus", str(world), "--steps", "5", "--sequences", str(args.sequences),
+                                   "--model", args.model, "--single-process-child", scores_file],
+                                  capture_output=True, text=True, timeout=600,
+                                  env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            result = json.loads(done.stdout.strip().splitlines()[-1]) if done.returncode == 0 else {
+                "error": f"child exited {done.returncode}: {done.stderr[-300:]}"}
+        except Exception as e:  # noqa: BLE001
+            result = {"error": f"{type(e).__name__}: {e}"[:300]}
+        store.set("msv_single_process_done", "1")
+    else:
+        store.wait(["msv_single_process_done"])
+    return result
+
+
 def main() -> None:
     args = parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    if args.single_process_child:
+        single_process_child(args)
+        return
+    single_process = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and args.scaling == "strong" and not args.no_side_keys:
+        single_process = single_process_before_ranks(args, int(os.environ.get("RANK", "0")), int(os.environ["WORLD_SIZE"]))
 
     import torch
     import torch.distributed as dist
@@ -690,49 +771,14 @@ def main() -> None:
                 (job[int(bounds[0]): int(bounds[1])].view(np.uint32) == result.view(np.uint32)).all())
             parity["e2e_job_buffer_has_no_gaps"] = bool(not np.isnan(job[:n_total]).any())
 
-    # ---- single process, all GPUs, through the C ABI (msv_cuda_multi_score_batch); the other ranks wait ----
-    # (an NCCL barrier would leave a spinning kernel from another PROCESS on every other GPU, and two processes time-slice
-    # a GPU: the waiting ranks therefore wait on the host, through the rendezvous store)
-    def host_barrier(tag: str) -> None:
-        store = dist.distributed_c10d._get_default_store()
-        store.add(tag, 1)
-        while int(store.add(tag, 0)) < world:
-            time.sleep(0.002)
-
-    single_process = None
-    if world > 1 and not args.no_side_keys and strong:
-        torch.cuda.synchronize()
-        host_barrier("single_process_begin")
-        if rank == 0:
-            single_process = {}
-            try:
-                replicas = [model] + [msv.Model(_cabi.emission_table(profile.match_emissions), *_cabi.model_transitions(profile.model_length),
-                                                device=g) for g in range(1, world)]
-                multi = _cabi.MultiGpu(replicas)
-                host_codes = torch.from_numpy(np.ascontiguousarray(all_codes)).pin_memory()
-                host_offsets = torch.from_numpy(np.ascontiguousarray(all_offsets).view(np.int64)).pin_memory()
-                out_scores = torch.empty(n_total, dtype=torch.float32).pin_memory()
-                for name, mode in (("host", _cabi.GATHER_HOST), ("peer", _cabi.GATHER_PEER), ("nccl", _cabi.GATHER_NCCL)):
-                    try:
-                        for _ in range(2):
-                            multi.score_batch(host_codes, host_offsets, out_scores, gather=mode)
-                        t0 = time.perf_counter()
-                        for _ in range(5):
-                            multi.score_batch(host_codes, host_offsets, out_scores, gather=mode)
-                        dt = (time.perf_counter() - t0) / 5
-                        same = bool((out_scores.numpy().view(np.uint32) == job_scores.numpy()[:n_total].view(np.uint32)).all())
-                        single_process[name] = {"e2e_gcups": round(cells_job / dt / 1e9, 1), "ms_per_step": round(dt * 1e3, 3),
-                                                "same_bits_as_multi_process_job_buffer": same}
-                    except Exception as e:  # noqa: BLE001
-                        single_process[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
-                single_process["api"] = "msv_cuda_multi_score_batch: one process, one host thread per GPU, pinned host database in, host scores out"
-                multi.close()
-                for m in replicas[1:]:
-                    m.close()
-            except Exception as e:  # noqa: BLE001
-                single_process = {"error": f"{type(e).__name__}: {e}"[:300]}
-        torch.cuda.synchronize()
-        host_barrier("single_process_done")
+    # ---- single process, all GPUs, through the C ABI: measured before the ranks started (single_process_before_ranks) ----
+    if single_process is not None and rank == 0 and strong and "scores_file" in single_process:
+        try:
+            theirs = np.load(single_process.pop("scores_file"))
+            single_process["same_bits_as_multi_process_job_buffer"] = bool(
+                theirs.size == n_total and (theirs.view(np.uint32) == job_scores.numpy()[:n_total].view(np.uint32)).all())
+        except Exception as e:  # noqa: BLE001
+            single_process["same_bits_as_multi_process_job_buffer"] = f"not compared: {type(e).__name__}: {e}"[:200]
 
     if rank == 0:
         value = cells_job * args.steps / (ms_total / 1e3) / 1e9

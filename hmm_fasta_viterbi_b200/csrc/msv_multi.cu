@@ -12,6 +12,9 @@
 // NCCL is bound at run time (dlopen of libnccl.so.2), so the library itself has no link-time dependency on it.
 #include <dlfcn.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <thread>
@@ -198,9 +201,12 @@ int msv_cuda_multi_score_batch(msv_multi* multi, const uint8_t* residues, const 
     // ---- one host thread per GPU: upload + bucket + scan of its slice (pipelined inside the call) ----
     std::vector<int> status(ngpu, MSV_OK);
     std::vector<std::string> message(ngpu);
+    const bool trace = std::getenv("MSV_MULTI_TRACE") != nullptr; // tuning aid: per-GPU wall time of the slice, on stderr
+    const auto call_begin = std::chrono::steady_clock::now();
     const auto work = [&](int g) {
         const size_t first = bounds[g], last = bounds[g + 1];
         if (first == last) return;
+        const auto begin = std::chrono::steady_clock::now();
         std::vector<uint64_t> local(offsets + first, offsets + last + 1); // the slice's offsets, rebased to its first residue
         const uint64_t base = local.front();
         for (auto& o : local) o -= base;
@@ -216,6 +222,12 @@ int msv_cuda_multi_score_batch(msv_multi* multi, const uint8_t* residues, const 
         if (rc != MSV_OK) {
             status[g] = rc;
             message[g] = msv_cuda_last_error();
+        }
+        if (trace) {
+            const auto end = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[msv_multi] GPU %d: %zu sequences, started %.3f ms into the call, took %.3f ms\n", multi->devices[g], last - first,
+                         std::chrono::duration<double, std::milli>(begin - call_begin).count(),
+                         std::chrono::duration<double, std::milli>(end - begin).count());
         }
     };
     {

@@ -19,6 +19,10 @@
  *   - there is no CPU fallback: without a CUDA device every msv_cuda_* call fails with MSV_ERR_NO_DEVICE.
  *   - thread safety: calls that share a msv_model or a msv_db must be serialised by the caller (the reference's
  *     MSV_HMM is not re-entrant either, MSV_HMM.cpp:59-64); distinct handles may be used from distinct threads.
+ *     The asynchronous entry points (msv_cuda_db_score_device, msv_cuda_db_score_gather, msv_cuda_db_viterbi_device,
+ *     msv_cuda_db_viterbi_subset_device) must ALSO be ordered on the device: scans of one msv_db share its work queue and
+ *     scratch lists, so two scans of the same database (with whatever models) must not overlap on the GPU -- launch them
+ *     on one stream, or order the streams with events.  Scans of different databases may overlap freely.
  */
 #ifndef MSV_CUDA_H
 #define MSV_CUDA_H

@@ -646,8 +646,10 @@ def test_fused_gather_two_gpus(tmp_path):
     checked = [v for k, v in line["parity"].items() if k.startswith("gathered_job_buffer_vs_")]
     assert checked and checked[0]["mismatches"] == 0 and checked[0]["checked"] >= 1000
     # ... and the single-process driver behind the C ABI (msv_cuda_multi_score_batch) gives the same bits in every gather mode
-    for mode in ("host", "peer", "nccl"):
-        assert line["single_process_multi_gpu"][mode].get("same_bits_as_multi_process_job_buffer") is True, line["single_process_multi_gpu"]
+    single = line["single_process_multi_gpu"]
+    assert single["same_bits_as_multi_process_job_buffer"] is True, single
+    for mode in ("peer", "nccl"):
+        assert single[mode].get("same_bits_as_first_mode") is True and single["host"]["e2e_gcups"] > 0, single
 
 
 # ---- speculative rows (B = N + move while J <= N) and their exact fallback ---------------------------------------------
