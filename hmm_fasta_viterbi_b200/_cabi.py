@@ -26,7 +26,7 @@ DECLARED_SYMBOLS = (
     "msv_cuda_abi_version", "msv_cuda_last_error", "msv_cuda_device_count",
     "msv_host_emission_table", "msv_host_model_transitions", "msv_host_length_transitions", "msv_host_encode",
     "msv_host_partition_by_cells",
-    "msv_cuda_model_create", "msv_cuda_model_destroy", "msv_cuda_model_geometry", "msv_cuda_model_plan", "msv_cuda_model_speculation",
+    "msv_cuda_model_create", "msv_cuda_model_destroy", "msv_cuda_model_geometry", "msv_cuda_model_plan", "msv_cuda_model_plan_long_sequences", "msv_cuda_model_speculation",
     "msv_cuda_db_create", "msv_cuda_db_destroy", "msv_cuda_db_info",
     "msv_cuda_db_score_device", "msv_cuda_db_score_gather", "msv_cuda_db_score", "msv_cuda_score_batch", "msv_cuda_score_sequence",
     "msv_cuda_db_filter_device", "msv_cuda_db_score_filter", "msv_cuda_host_register", "msv_cuda_host_unregister",
@@ -74,6 +74,7 @@ lib.msv_cuda_model_destroy.argtypes = [C.c_void_p]
 lib.msv_cuda_model_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                         C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
 lib.msv_cuda_model_plan.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+lib.msv_cuda_model_plan_long_sequences.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_int), C.POINTER(C.c_int)]
 lib.msv_cuda_model_speculation.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_int)]
 lib.msv_cuda_db_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
 lib.msv_cuda_db_destroy.argtypes = [C.c_void_p]
@@ -260,7 +261,12 @@ class Model:
         """Launch plan a scan of `database` would use: kernel family (lanes per sequence) and sequences per CTA."""
         lanes, per_cta = C.c_int(), C.c_int()
         check(lib.msv_cuda_model_plan(self.handle, database.handle, C.byref(lanes), C.byref(per_cta)))
-        return {"lanes_per_sequence": lanes.value, "sequences_per_cta": per_cta.value}
+        n_long, fast_ctas, fast_slots = C.c_uint(), C.c_int(), C.c_int()
+        check(lib.msv_cuda_model_plan_long_sequences(self.handle, database.handle, C.byref(n_long), C.byref(fast_ctas), C.byref(fast_slots)))
+        plan = {"lanes_per_sequence": lanes.value, "sequences_per_cta": per_cta.value}
+        if fast_ctas.value:  # lane-group plans: the longest sequences on a few CTAs with fewer, faster slots
+            plan |= {"long_sequences": n_long.value, "fast_ctas": fast_ctas.value, "fast_sequences_per_cta": fast_slots.value}
+        return plan
 
     def score_batch(self, residues, offsets, out=None) -> np.ndarray:
         """End-to-end call with host buffers (numpy arrays or pinned torch tensors)."""

@@ -311,7 +311,6 @@ int db_release(msv_db* db) {
     cudaFree(db->d_offsets);
     cudaFree(db->d_order);
     cudaFree(db->d_scores);
-    cudaFree(db->d_redo);
     cudaFree(db->d_stats);
     cudaFree(db->d_length_tr);
     cudaFree(db->d_hist);
@@ -363,22 +362,19 @@ int db_reserve(msv_db* db, uint64_t total, size_t n, uint64_t longest, cudaStrea
         cudaFree(db->d_offsets);
         cudaFree(db->d_order);
         cudaFree(db->d_scores);
-        cudaFree(db->d_redo);
         db->d_offsets = nullptr;
         db->d_order = nullptr;
         db->d_scores = nullptr;
-        db->d_redo = nullptr;
         db->cap_n = 0;
         const size_t cap = n + 1 + n / 8;
         MSV_CUDA_TRY(cudaMalloc(&db->d_offsets, cap * sizeof(uint64_t)));
         MSV_CUDA_TRY(cudaMalloc(&db->d_order, cap * sizeof(uint32_t)));
         MSV_CUDA_TRY(cudaMalloc(&db->d_scores, cap * sizeof(float)));
-        MSV_CUDA_TRY(cudaMalloc(&db->d_redo, cap * sizeof(uint32_t)));
         db->cap_n = cap;
     }
     if (!db->d_hist) {
         MSV_CUDA_TRY(cudaMalloc(&db->d_hist, 2 * kBuckets * sizeof(uint32_t)));
-        MSV_CUDA_TRY(cudaMalloc(&db->d_queue, 3 * kMaxChunks * sizeof(unsigned int))); // queue heads | redo counts | redo queue heads
+        MSV_CUDA_TRY(cudaMalloc(&db->d_queue, 2 * kMaxChunks * sizeof(unsigned int))); // per upload stage: queue head, head of its second part (next_ticket)
         MSV_CUDA_TRY(cudaMalloc(&db->d_first_bad, sizeof(unsigned long long)));
     }
     if (db->h_length_tr.size() < longest + 1) {
@@ -401,7 +397,7 @@ int db_reserve(msv_db* db, uint64_t total, size_t n, uint64_t longest, cudaStrea
     }
     const unsigned long long none = ~0ull;
     MSV_CUDA_TRY(cudaMemcpyAsync(db->d_first_bad, &none, sizeof none, cudaMemcpyHostToDevice, stream));
-    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, 3 * kMaxChunks * sizeof(unsigned int), stream));
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue, 0, 2 * kMaxChunks * sizeof(unsigned int), stream));
     return MSV_OK;
 }
 
@@ -450,10 +446,31 @@ int db_read_validation(msv_db* db, const uint8_t* residues, cudaStream_t stream)
     return MSV_OK;
 }
 
-// Small databases keep their lengths on the host: the launch planner needs them to balance few long sequences.
+// Sequences and rows per bucket of kProfileStep lengths for sequences [first, first + count) (see msv_db::h_profile_*).
+struct Length_profile {
+    const uint32_t* count = nullptr;
+    const uint64_t* rows = nullptr;
+};
+void profile_lengths(const uint64_t* offsets, size_t first, size_t count, std::vector<uint32_t>& counts, std::vector<uint64_t>& rows) {
+    counts.assign(kProfileBuckets, 0);
+    rows.assign(kProfileBuckets, 0);
+    for (size_t q = first; q < first + count; ++q) {
+        const uint64_t len = offsets[q + 1] - offsets[q];
+        const size_t bucket = static_cast<size_t>(std::min<uint64_t>(len / kProfileStep, kProfileBuckets - 1));
+        ++counts[bucket];
+        rows[bucket] += len;
+    }
+}
+
+// Small databases keep their lengths on the host: the launch planner needs them to balance few long sequences.  Every
+// database whose offsets pass through the host keeps its length profile.
 void db_keep_lengths(msv_db* db, const uint64_t* offsets, size_t n) {
     db->h_lengths.clear();
-    if (n == 0 || n > 65536) return;
+    db->h_profile_count.clear();
+    db->h_profile_rows.clear();
+    if (n == 0) return;
+    profile_lengths(offsets, 0, n, db->h_profile_count, db->h_profile_rows);
+    if (n > 65536) return;
     db->h_lengths.resize(n);
     for (size_t q = 0; q < n; ++q) db->h_lengths[q] = static_cast<uint32_t>(offsets[q + 1] - offsets[q]);
 }
@@ -501,6 +518,8 @@ namespace {
 struct Launch_plan {
     const msv_model::Plan* plan;
     size_t slots_per_cta;
+    // lane-group plans: the n_long longest sequences go to fast_ctas CTAs that run with fast_slots slots (next_ticket)
+    uint32_t n_long = 0, fast_ctas = 0, fast_slots = 0;
 };
 
 // throughput of the warp kernel at `fraction` of its maximum warps per SM (measured: 25 % -> 0.51, 50 % -> 0.885, 75 % -> 0.98)
@@ -533,7 +552,44 @@ uint64_t lpt_makespan(const std::vector<uint32_t>& lengths, size_t slots) {
     return *std::max_element(heap.begin(), heap.end());
 }
 
-Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, size_t count, uint64_t residues) {
+// Lane-group plans: which sequences are too long for a slot of a full CTA, and how many fast CTAs they need.
+// A slot of a full CTA scans `average` rows in the time of the whole launch; a slot of a fast CTA (warps_fast of
+// warps_full warps, measured throughput `relative`) scans relative * warps_full / warps_fast times as many.
+bool plan_fast_ctas(const Length_profile& profile, uint64_t residues, uint64_t longest, size_t sms, size_t slots_full, size_t per_warp,
+                    Launch_plan& plan) {
+    const uint64_t average = residues / (sms * slots_full); // rows per slot of a balanced launch
+    const size_t warps_full = slots_full / per_warp;
+    int want_ctas = 0, want_warps = 0, want_cut = 0; // MSV_CUDA_FAST_CTAS="ctas,warps,rows" (tuning aid)
+    if (const char* env = std::getenv("MSV_CUDA_FAST_CTAS")) std::sscanf(env, "%d,%d,%d", &want_ctas, &want_warps, &want_cut);
+    if (!want_ctas && 10 * average >= 12 * std::max<uint64_t>(longest, 1)) return true; // nothing is too long: plain queue, all slots
+    for (const size_t warps_fast : {size_t(8), size_t(4)}) {
+        if (want_warps ? warps_fast != static_cast<size_t>(want_warps) : warps_fast * 2 > warps_full) continue;
+        // throughput of a CTA at that occupancy relative to a full one (B200, profiles/r02/short_model_sweep_v1.jsonl:
+        // 8 warps 0.69..0.90, 4 warps about half)
+        const double relative = warps_fast == 8 ? 0.75 : 0.5;
+        const double speedup = relative * static_cast<double>(warps_full) / static_cast<double>(warps_fast);
+        if (!want_warps && static_cast<double>(longest) > 0.95 * speedup * static_cast<double>(average)) continue;
+        // long = at least 0.8 x the rows of an average slot, at a bucket boundary of the profile
+        const uint64_t cut = want_cut ? static_cast<uint64_t>(want_cut) / kProfileStep * kProfileStep
+                                      : std::max<uint64_t>(2 * kProfileStep, average * 8 / 10 / kProfileStep * kProfileStep);
+        if (cut / kProfileStep >= kProfileBuckets) continue;
+        uint64_t n_long = 0, rows_long = 0;
+        for (size_t b = cut / kProfileStep; b < kProfileBuckets; ++b) n_long += profile.count[b], rows_long += profile.rows[b];
+        if (n_long == 0) return true;
+        const double share = static_cast<double>(rows_long) / static_cast<double>(residues);
+        const size_t ctas = want_ctas ? static_cast<size_t>(want_ctas)
+                                      : static_cast<size_t>(std::ceil(1.15 * share / relative * static_cast<double>(sms)));
+        if (ctas < 1 || 2 * ctas > sms) continue;
+        plan.n_long = static_cast<uint32_t>(n_long);
+        plan.fast_ctas = static_cast<uint32_t>(ctas);
+        plan.fast_slots = static_cast<uint32_t>(warps_fast * per_warp);
+        return true;
+    }
+    return false;
+}
+
+Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, size_t count, uint64_t residues,
+                        const Length_profile* profile = nullptr) {
     const auto max_slots = [](const msv_model::Plan& plan) { return static_cast<size_t>(plan.geo->threads / plan.geo->G); };
     if (!model->bulk.geo) return {&model->quad, max_slots(model->quad)};
     if (model->forced) return {&model->bulk, max_slots(model->bulk)};
@@ -553,10 +609,16 @@ Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, 
         // (profiles/r02/short_model_sweep_v1.jsonl, 100.hmm x 100 k sequences, four lanes per sequence): 192 slots per CTA
         // 5.0 TCUPS, 96: 6.3, 64: 6.6, 48: 5.9; with 1 M sequences every slot count is balanced and the maximum wins (7.5).
         // Four lanes per sequence beat eight wherever both exist (100.hmm 7.5 vs 6.2, 200.hmm 8.4 vs 7.6 TCUPS at 1 M).
+        // Round 2: when the length profile of the range is known, all CTAs but a few keep every slot and the longest
+        // sequences go to a few fast CTAs instead (plan_fast_ctas / next_ticket); the cut is the fallback.
         for (const msv_model::Plan* plan : {&model->narrow, &model->octet}) {
             if (!plan->geo) continue;
             const size_t per_warp = 32 / static_cast<size_t>(plan->geo->G);
             const size_t most = max_slots(*plan), least = std::max(per_warp, most / 3 / per_warp * per_warp);
+            if (profile && profile->count && count >= 2 * sms * most && !std::getenv("MSV_CUDA_NO_FAST_CTAS")) {
+                Launch_plan chosen{plan, most};
+                if (plan_fast_ctas(*profile, residues, db->longest, sms, most, per_warp, chosen)) return chosen;
+            }
             for (size_t slots = most; slots >= least; slots -= per_warp)
                 if (10 * (residues / (sms * slots)) >= 12 * std::max<uint64_t>(db->longest, 1)) return {plan, slots};
         }
@@ -589,10 +651,16 @@ Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, 
 }
 
 // One launch of the scan over sequences [first, first+count) of `db`; scores go to d_scores[first ..).
+Length_profile whole_profile(const msv_db* db) { // of the whole database, when its offsets passed through the host
+    if (db->h_profile_count.size() != kProfileBuckets) return {};
+    return {db->h_profile_count.data(), db->h_profile_rows.data()};
+}
+
 int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64_t residues, int queue_slot, float* d_scores,
-                cudaStream_t stream, float* const* mirrors = nullptr, int n_mirrors = 0) {
+                cudaStream_t stream, float* const* mirrors = nullptr, int n_mirrors = 0, const Length_profile* stage_profile = nullptr) {
     if (count == 0) return MSV_OK;
-    const Launch_plan chosen = plan_launch(model, db, first, count, residues);
+    const Length_profile whole = (first == 0 && count == db->n) ? whole_profile(db) : Length_profile{};
+    const Launch_plan chosen = plan_launch(model, db, first, count, residues, stage_profile ? stage_profile : &whole);
     const msv_model::Plan& plan = *chosen.plan;
     const Geometry* geo = plan.geo;
     msv::Scan_params p{};
@@ -602,7 +670,7 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     p.order = db->d_order + first;
     p.length_tr = db->d_length_tr;
     p.scores = d_scores + first;
-    p.queue_head = db->d_queue + queue_slot;
+    p.queue_head = db->d_queue + 2 * queue_slot;
     p.first_bad = db->d_first_bad;
     p.n = static_cast<uint32_t>(count);
     p.table_bytes = static_cast<uint32_t>(plan.shared_bytes);
@@ -611,7 +679,7 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     p.tr_E_J = model->tr_E_J;
     p.n_mirrors = static_cast<uint32_t>(n_mirrors);
     for (int r = 0; r < n_mirrors; ++r) p.mirrors[r] = mirrors[r] + first;
-    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue + queue_slot, 0, sizeof(unsigned int), stream));
+    MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue + 2 * queue_slot, 0, 2 * sizeof(unsigned int), stream));
     // persistent CTAs, at most one per SM; a "slot" scans one sequence at a time (lane group, warp or four warps)
     const size_t threads_per_slot = static_cast<size_t>(geo->G);
     size_t slots = std::min<size_t>(chosen.slots_per_cta, geo->threads / threads_per_slot);
@@ -623,6 +691,11 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     const bool cj_same = std::memcmp(&model->tr_E_C, &model->tr_E_J, sizeof(float)) == 0;
     const bool group_speculation = geo->fn_group_spec && cj_same && residues / count <= 2048 && count >= 4096 &&
                                    !std::getenv("MSV_CUDA_NO_SPECULATION");
+    if (chosen.fast_ctas && chosen.fast_ctas < ctas && chosen.fast_slots < slots) {
+        p.n_long = chosen.n_long;
+        p.fast_ctas = chosen.fast_ctas;
+        p.fast_threads = static_cast<uint32_t>(chosen.fast_slots * threads_per_slot);
+    }
     if (group_speculation) { // lane groups with speculative rows; a sequence whose speculation fails is repeated exactly in the kernel
         geo->fn_group_spec<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
         ++g_launches;
@@ -707,6 +780,8 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
         if (bounds[stages] < n || stages == 0) bounds[++stages] = n;
     }
 
+    std::vector<uint32_t> stage_counts;
+    std::vector<uint64_t> stage_rows;
     const auto enqueue = [&]() -> int {
         MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy));
         MSV_CUDA_TRY(cudaMemsetAsync(db->d_residues + total, 0, msv::kResiduePadBytes + 16, copy));
@@ -718,7 +793,14 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
             MSV_CUDA_TRY(cudaEventRecord(db->stage_copied[s], copy));
             MSV_CUDA_TRY(cudaStreamWaitEvent(compute, db->stage_copied[s], 0));
             if (int rc = db_prepare_range(db, first, last - first, begin, end, longest, compute)) return rc;
-            if (int rc = launch_scan(model, db, first, last - first, end - begin, s, d_out, compute, mirrors, n_mirrors)) return rc;
+            Length_profile stage_profile;
+            if (stages > 1 && (model->narrow.geo || model->octet.geo)) { // lane-group plans want to know the long sequences of the stage
+                profile_lengths(offsets, first, last - first, stage_counts, stage_rows);
+                stage_profile = {stage_counts.data(), stage_rows.data()};
+            }
+            if (int rc = launch_scan(model, db, first, last - first, end - begin, s, d_out, compute, mirrors, n_mirrors,
+                                     stage_profile.count ? &stage_profile : nullptr))
+                return rc;
         }
         if (scores_host) MSV_CUDA_TRY(cudaMemcpyAsync(scores_host, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, compute));
         return db_read_validation(db, residues, compute);
@@ -1194,9 +1276,20 @@ int msv_cuda_model_speculation(const msv_model* model, unsigned int* failed, uns
 
 int msv_cuda_model_plan(const msv_model* model, const msv_db* db, int* lanes_per_sequence, int* sequences_per_cta) {
     if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
-    const Launch_plan chosen = plan_launch(model, db, 0, db->n, db->total);
+    const Length_profile whole = whole_profile(db);
+    const Launch_plan chosen = plan_launch(model, db, 0, db->n, db->total, &whole);
     if (lanes_per_sequence) *lanes_per_sequence = chosen.plan->geo->G;
     if (sequences_per_cta) *sequences_per_cta = static_cast<int>(chosen.slots_per_cta);
+    return MSV_OK;
+}
+
+int msv_cuda_model_plan_long_sequences(const msv_model* model, const msv_db* db, unsigned int* n_long, int* fast_ctas, int* fast_sequences_per_cta) {
+    if (!model || !db) return fail(MSV_ERR_INVALID_ARGUMENT, "NULL handle");
+    const Length_profile whole = whole_profile(db);
+    const Launch_plan chosen = plan_launch(model, db, 0, db->n, db->total, &whole);
+    if (n_long) *n_long = chosen.n_long;
+    if (fast_ctas) *fast_ctas = static_cast<int>(chosen.fast_ctas);
+    if (fast_sequences_per_cta) *fast_sequences_per_cta = static_cast<int>(chosen.fast_slots);
     return MSV_OK;
 }
 

@@ -27,15 +27,32 @@ struct Scan_params {
     // into this GPU's address space over NVLink; already offset to this shard's first sequence).  0 = plain scan.
     uint32_t n_mirrors;
     float* mirrors[kMaxScoreMirrors];
-    // speculative lane-group scan: sequences whose speculation failed are appended here and scanned by an exact pass that
-    // takes its sequence count from device memory (n_device, when not NULL, replaces n)
-    uint32_t* redo_list;
-    unsigned int* redo_count;
-    const unsigned int* n_device;
+    // lane-group kernels, long sequences on fast CTAs (see next_ticket): the first n_long entries of `order` (the longest
+    // sequences) are handed to CTAs [0, fast_ctas), which run with fast_threads threads only -- fewer, faster slots --
+    // while the other CTAs start behind them; queue_head[1] is the cursor of that second part.  n_long = 0: one plain queue.
+    uint32_t n_long, fast_ctas, fast_threads;
     // running totals for the host's choice of the speculation mode (may be NULL): [0] sequences whose speculation failed,
     // [1] sequences offered to a speculating warp kernel
     unsigned int* speculation_failures;
 };
+
+// Work queue of the lane-group kernels.  `order` lists the sequences longest first.  A lane group scans a sequence at 1/slots
+// of its SM's speed, so on a CTA with hundreds of slots the few longest sequences of a database would finish long after
+// everything else (3000 rows at ~530 clocks per row against ~0.5 ms for the whole scan of 100 k sequences).  Cutting the slot
+// count of EVERY CTA (what the planner did before) trades throughput for it everywhere; instead a few "fast" CTAs run with
+// a fraction of the threads, take the long sequences first (tickets [0, n_long)) and carry on with the rest, while the full
+// CTAs work through tickets [n_long, n) and only help with long ones when nothing else is left.
+__device__ __forceinline__ uint32_t next_ticket(const Scan_params& p, const bool fast_cta) {
+    if (p.n_long == 0) return atomicAdd(p.queue_head, 1u);
+    if (fast_cta) {
+        const uint32_t t = atomicAdd(p.queue_head, 1u);
+        if (t < p.n_long) return t;
+    }
+    const uint32_t t = p.n_long + atomicAdd(p.queue_head + 1, 1u);
+    if (t < p.n || fast_cta) return t;
+    const uint32_t late = atomicAdd(p.queue_head, 1u);
+    return late < p.n_long ? late : p.n;
+}
 
 // the one store per sequence: local result plus, for the fused gather, the same 4 bytes into every peer's array
 __device__ __forceinline__ void store_score(const Scan_params& p, uint32_t idx, float score) {

@@ -39,6 +39,7 @@ struct Device_guard {
 
 // ---- device-resident database (opaque handle of the C ABI) --------------------------------------------------------------
 constexpr int kMaxChunks = 32; // pipelined upload: at most this many upload/scan stages per batch
+constexpr uint32_t kProfileStep = 32, kProfileBuckets = 2048; // host length profile: 32-row buckets up to 65 504 rows
 struct msv_db {
     int device = 0;
     size_t n = 0;
@@ -50,7 +51,6 @@ struct msv_db {
     uint64_t* d_offsets = nullptr;
     uint32_t* d_order = nullptr;
     float* d_scores = nullptr;
-    uint32_t* d_redo = nullptr; // sequences a speculative lane-group scan hands to its exact pass (cap_n entries)
     float* d_stats = nullptr; // bit scores | P-values, 2 * cap_n, allocated on first use
     size_t cap_stats = 0;
     size_t cap_n = 0;
@@ -61,6 +61,11 @@ struct msv_db {
     unsigned long long* d_first_bad = nullptr;
     std::vector<float2> h_length_tr; // host copy, extended lazily
     std::vector<uint32_t> h_lengths; // sequence lengths, kept on the host only for small databases (launch planning)
+    // length profile of the whole database for the launch planner (lane-group plans put the longest sequences on fast
+    // CTAs): sequences and rows per bucket of kProfileStep lengths, the last bucket open-ended; empty when the offsets
+    // never were on the host (databases parsed on the device)
+    std::vector<uint32_t> h_profile_count;
+    std::vector<uint64_t> h_profile_rows;
     // pipelined upload (msv_cuda_score_batch): copy engine and scan overlap
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     cudaEvent_t stage_copied[kMaxChunks] = {};

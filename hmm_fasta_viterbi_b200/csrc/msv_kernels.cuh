@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
         }
     }
     mbarrier_wait(&table_ready, 0);
+    const bool fast_cta = blockIdx.x < p.fast_ctas;
+    if (fast_cta && threadIdx.x >= p.fast_threads) return; // whole warps; nobody meets at a barrier after this point
 
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
@@ -82,7 +84,6 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
     const uint32_t tab_lane = smem_u32(smem_raw) + (lane & (LANES_PER_QUAD_ROW - 1)) * 16;
     const float NEG_INF = __int_as_float(0xff800000);
     const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
-    const uint32_t n_sequences = p.n_device ? *p.n_device : p.n; // the exact pass after a speculative scan reads its count here
 
     float m[K];
 #pragma unroll
@@ -102,9 +103,9 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
                 active = false;
             }
             uint32_t ticket = 0;
-            if (gl == 0) ticket = atomicAdd(p.queue_head, 1u);
+            if (gl == 0) ticket = next_ticket(p, fast_cta);
             ticket = __shfl_sync(gmask, ticket, 0, G);
-            if (ticket >= n_sequences) {
+            if (ticket >= p.n) {
                 done = true;
                 buf = 0;
                 nextw = 0;
@@ -209,6 +210,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
         }
     }
     mbarrier_wait(&table_ready, 0);
+    const bool fast_cta = blockIdx.x < p.fast_ctas;
+    if (fast_cta && threadIdx.x >= p.fast_threads) return; // whole warps; nobody meets at a barrier after this point
 
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
                 active = false;
             }
             uint32_t ticket = 0;
-            if (gl == 0) ticket = atomicAdd(p.queue_head, 1u);
+            if (gl == 0) ticket = next_ticket(p, fast_cta);
             ticket = __shfl_sync(gmask, ticket, 0, G);
             if (ticket >= p.n) {
                 done = true;

@@ -110,6 +110,12 @@ int msv_cuda_model_speculation(const msv_model* model, unsigned int* failed, uns
 /* which launch plan a scan of the whole of `db` with `model` would use (introspection for tests and tuning): lanes per
  * sequence of the chosen kernel family (8, 32 or 128) and sequences in flight per CTA.  Does not launch anything. */
 int msv_cuda_model_plan(const msv_model* model, const msv_db* db, int* lanes_per_sequence, int* sequences_per_cta);
+/* ... and, for the lane-group plans of short models, how that scan would treat the longest sequences: a lane group scans a
+ * sequence at 1/sequences_per_cta of its SM's speed, so the *n_long longest sequences (0 = none need it) are handed to
+ * *fast_ctas CTAs that run only *fast_sequences_per_cta sequences at a time, while all other CTAs keep every slot busy with
+ * the rest.  Known only for databases whose offsets passed through the host (not for msv_cuda_db_create_from_fasta). */
+int msv_cuda_model_plan_long_sequences(const msv_model* model, const msv_db* db, unsigned int* n_long, int* fast_ctas,
+                                       int* fast_sequences_per_cta);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Database (device resident).  Uploads residues + offsets, validates the codes, computes the per-length

@@ -226,8 +226,10 @@ def test_launch_planner_choices(oracle):
     assert big.plan(many_db) == {"lanes_per_sequence": 32, "sequences_per_cta": 16}      # bulk: a warp each, 16 warps per SM
     assert short.plan(many_db)["lanes_per_sequence"] == 8                                # short model, many sequences: 8 lanes each
     shortest, _, _ = device_model(oracle, "100.hmm")
-    plan = shortest.plan(many_db)                                                        # the shortest models: 4 lanes each, and
-    assert plan["lanes_per_sequence"] == 4 and 64 <= plan["sequences_per_cta"] < 192     # fewer slots than the maximum at this size
+    plan = shortest.plan(many_db)                                                        # the shortest models: 4 lanes each, every
+    assert plan["lanes_per_sequence"] == 4 and plan["sequences_per_cta"] == 192          # slot in use, and the longest sequences on
+    assert 0 < plan["fast_ctas"] < 74 and plan["fast_sequences_per_cta"] in (32, 64)     # a few CTAs with fewer, faster slots
+    assert 0 < plan["long_sequences"] < 15_000
     titin = msv.Packed_sequences.synthetic_long_uniform(2048, 2405, 10_000, 35_000)     # config 5: fewer sequences than warp slots
     plan = big.plan(msv.Database(titin.residues, titin.offsets))
     assert plan["lanes_per_sequence"] == 32 and plan["sequences_per_cta"] in (8, 12)     # a warp each at reduced occupancy
@@ -245,6 +247,35 @@ def test_few_long_sequences_use_four_warps_each(oracle):
     assert ubits(model.score_batch(codes, offsets)).tolist() == ubits(want).tolist()
     db = msv.Database(codes, offsets)
     assert ubits(db.score(model)).tolist() == ubits(want).tolist()
+
+
+@pytest.mark.parametrize("name", ["100.hmm", "200.hmm", "300.hmm", "400.hmm"])
+def test_long_sequences_on_fast_ctas(oracle, name, monkeypatch):
+    """Lane-group plans (short models): the longest sequences of a database are handed to a few CTAs with fewer, faster slots
+    (next_ticket in msv_device.cuh).  Same bits as the plain queue, as the oracle, through the resident and the pipelined
+    end-to-end path (whose upload stages are planned one by one), and for a forced, lopsided split."""
+    model, table, tr3 = device_model(oracle, name)
+    packed = msv.Packed_sequences.synthetic_swissprot_like(120_000, 77)
+    codes, offsets = packed.residues, packed.offsets
+    db = msv.Database(codes, offsets)
+    plan = model.plan(db)
+    assert plan["lanes_per_sequence"] in (4, 8) and plan.get("fast_ctas", 0) > 0, plan
+    got = db.score(model)
+    rng = np.random.default_rng(5)
+    longest = np.argsort(np.diff(offsets.astype(np.int64)))[-40:]
+    sample = np.concatenate([rng.choice(len(packed), size=400, replace=False), longest])
+    sc, so = pack([codes[int(offsets[q]):int(offsets[q + 1])] for q in sample])
+    want = oracle.score_batch(table, tr3, sc, so, threads=CORES)
+    assert ubits(got[sample]).tolist() == ubits(want).tolist()
+    assert (ubits(model.score_batch(codes, offsets)) == ubits(got)).all()
+    monkeypatch.setenv("MSV_CUDA_FAST_CTAS", "40,4,128")  # 40 CTAs, one warp per scheduler, everything from 128 rows up is "long"
+    assert (ubits(db.score(model)) == ubits(got)).all()
+    monkeypatch.setenv("MSV_CUDA_FAST_CTAS", "1,8,2048")  # one fast CTA: the full CTAs have to help with the long ones at the end
+    assert (ubits(db.score(model)) == ubits(got)).all()
+    monkeypatch.delenv("MSV_CUDA_FAST_CTAS")
+    monkeypatch.setenv("MSV_CUDA_NO_FAST_CTAS", "1")
+    assert "fast_ctas" not in model.plan(db)
+    assert (ubits(db.score(model)) == ubits(got)).all()
 
 
 def test_short_model_large_database_uses_eight_lanes_per_sequence(oracle):

@@ -27,6 +27,8 @@ def main() -> None:
     ap.add_argument("--long", action="store_true", help="config-5 style database (L ~ U[10000, 35000])")
     ap.add_argument("--check", type=int, default=200, help="sequences compared with the oracle per geometry")
     ap.add_argument("--slots", nargs="+", type=int, default=[0], help="sequences in flight per CTA (MSV_CUDA_BULK_SLOTS; 0 = the plan's own)")
+    ap.add_argument("--fast", nargs="+", default=["auto"],
+                    help='lane-group plans, long sequences on fast CTAs: "auto", "off" or "ctas,warps,rows" (MSV_CUDA_FAST_CTAS)')
     args = ap.parse_args()
 
     import torch
@@ -69,11 +71,17 @@ def main() -> None:
         except Exception as e:  # noqa: BLE001
             print(json.dumps({"geometry": geo, "error": str(e)}))
             continue
-        for slots in args.slots:
+        for slots, fast in [(s, f) for s in args.slots for f in args.fast]:
             if slots:
                 os.environ["MSV_CUDA_BULK_SLOTS"] = str(slots)
             else:
                 os.environ.pop("MSV_CUDA_BULK_SLOTS", None)
+            os.environ.pop("MSV_CUDA_FAST_CTAS", None)
+            os.environ.pop("MSV_CUDA_NO_FAST_CTAS", None)
+            if fast == "off":
+                os.environ["MSV_CUDA_NO_FAST_CTAS"] = "1"
+            elif fast != "auto":
+                os.environ["MSV_CUDA_FAST_CTAS"] = fast
             for _ in range(2):
                 db.score_device(model, scores, stream.cuda_stream)
             torch.cuda.synchronize()
@@ -86,10 +94,11 @@ def main() -> None:
             ms = t0.elapsed_time(t1) / args.steps
             got = scores.cpu().numpy()[sample]
             bad = int((got.view(np.uint32) != want.view(np.uint32)).sum())
-            print(json.dumps({"model": args.model, "sequences": args.sequences, "geometry": geo, "slots": slots, "plan": model.plan(db),
+            print(json.dumps({"model": args.model, "sequences": args.sequences, "geometry": geo, "slots": slots, "fast": fast, "plan": model.plan(db),
                               "chosen": model.geometry, "ms": round(ms, 3), "gcups": round(cells / ms / 1e6, 1),
                               "cells_per_clk_per_sm": round(cells / (ms * 1e-3) / 148 / 1.965e9, 2), "mismatches": bad}), flush=True)
-        os.environ.pop("MSV_CUDA_BULK_SLOTS", None)
+        for name in ("MSV_CUDA_BULK_SLOTS", "MSV_CUDA_FAST_CTAS", "MSV_CUDA_NO_FAST_CTAS"):
+            os.environ.pop(name, None)
         model.close()
 
 
