@@ -463,13 +463,13 @@ void profile_lengths(const uint64_t* offsets, size_t first, size_t count, std::v
 }
 
 // Small databases keep their lengths on the host: the launch planner needs them to balance few long sequences.  Every
-// database whose offsets pass through the host keeps its length profile.
+// database whose offsets pass through the host can keep its length profile.
 void db_keep_lengths(msv_db* db, const uint64_t* offsets, size_t n) {
     db->h_lengths.clear();
     db->h_profile_count.clear();
     db->h_profile_rows.clear();
     if (n == 0) return;
-    profile_lengths(offsets, 0, n, db->h_profile_count, db->h_profile_rows);
+    if (std::getenv("MSV_CUDA_FAST_CTAS")) profile_lengths(offsets, 0, n, db->h_profile_count, db->h_profile_rows); // (experiment, see plan_launch)
     if (n > 65536) return;
     db->h_lengths.resize(n);
     for (size_t q = 0; q < n; ++q) db->h_lengths[q] = static_cast<uint32_t>(offsets[q + 1] - offsets[q]);
@@ -559,7 +559,7 @@ bool plan_fast_ctas(const Length_profile& profile, uint64_t residues, uint64_t l
                     Launch_plan& plan) {
     const uint64_t average = residues / (sms * slots_full); // rows per slot of a balanced launch
     const size_t warps_full = slots_full / per_warp;
-    int want_ctas = 0, want_warps = 0, want_cut = 0; // MSV_CUDA_FAST_CTAS="ctas,warps,rows" (tuning aid)
+    int want_ctas = 0, want_warps = 0, want_cut = 0; // MSV_CUDA_FAST_CTAS="ctas,warps,rows", or "auto" for the model below
     if (const char* env = std::getenv("MSV_CUDA_FAST_CTAS")) std::sscanf(env, "%d,%d,%d", &want_ctas, &want_warps, &want_cut);
     if (!want_ctas && 10 * average >= 12 * std::max<uint64_t>(longest, 1)) return true; // nothing is too long: plain queue, all slots
     for (const size_t warps_fast : {size_t(8), size_t(4)}) {
@@ -609,13 +609,16 @@ Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, 
         // (profiles/r02/short_model_sweep_v1.jsonl, 100.hmm x 100 k sequences, four lanes per sequence): 192 slots per CTA
         // 5.0 TCUPS, 96: 6.3, 64: 6.6, 48: 5.9; with 1 M sequences every slot count is balanced and the maximum wins (7.5).
         // Four lanes per sequence beat eight wherever both exist (100.hmm 7.5 vs 6.2, 200.hmm 8.4 vs 7.6 TCUPS at 1 M).
-        // Round 2: when the length profile of the range is known, all CTAs but a few keep every slot and the longest
-        // sequences go to a few fast CTAs instead (plan_fast_ctas / next_ticket); the cut is the fallback.
+        // Round 2 experiment, NOT the default: keep every slot on most CTAs and hand the longest sequences to a few fast
+        // CTAs instead (plan_fast_ctas / next_ticket).  Measured on B200 over 60 settings (profiles/r02/fast_cta_sweep_v1..3.jsonl,
+        // 100..400.hmm x 100 k sequences): within -9 .. +3 % of the slot cut and never clearly ahead -- what the full CTAs
+        // lose at this database size is not only the longest sequences.  MSV_CUDA_FAST_CTAS="ctas,warps,rows" (or "auto")
+        // switches it on for further tuning; results are the same bits either way (test_long_sequences_on_fast_ctas).
         for (const msv_model::Plan* plan : {&model->narrow, &model->octet}) {
             if (!plan->geo) continue;
             const size_t per_warp = 32 / static_cast<size_t>(plan->geo->G);
             const size_t most = max_slots(*plan), least = std::max(per_warp, most / 3 / per_warp * per_warp);
-            if (profile && profile->count && count >= 2 * sms * most && !std::getenv("MSV_CUDA_NO_FAST_CTAS")) {
+            if (profile && profile->count && count >= 2 * sms * most && std::getenv("MSV_CUDA_FAST_CTAS")) {
                 Launch_plan chosen{plan, most};
                 if (plan_fast_ctas(*profile, residues, db->longest, sms, most, per_warp, chosen)) return chosen;
             }
@@ -794,7 +797,7 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
             MSV_CUDA_TRY(cudaStreamWaitEvent(compute, db->stage_copied[s], 0));
             if (int rc = db_prepare_range(db, first, last - first, begin, end, longest, compute)) return rc;
             Length_profile stage_profile;
-            if (stages > 1 && (model->narrow.geo || model->octet.geo)) { // lane-group plans want to know the long sequences of the stage
+            if (stages > 1 && (model->narrow.geo || model->octet.geo) && std::getenv("MSV_CUDA_FAST_CTAS")) { // (experiment, see plan_launch)
                 profile_lengths(offsets, first, last - first, stage_counts, stage_rows);
                 stage_profile = {stage_counts.data(), stage_rows.data()};
             }

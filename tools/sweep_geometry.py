@@ -27,7 +27,7 @@ def main() -> None:
     ap.add_argument("--long", action="store_true", help="config-5 style database (L ~ U[10000, 35000])")
     ap.add_argument("--check", type=int, default=200, help="sequences compared with the oracle per geometry")
     ap.add_argument("--slots", nargs="+", type=int, default=[0], help="sequences in flight per CTA (MSV_CUDA_BULK_SLOTS; 0 = the plan's own)")
-    ap.add_argument("--fast", nargs="+", default=["auto"],
+    ap.add_argument("--fast", nargs="+", default=["off"],
                     help='lane-group plans, long sequences on fast CTAs: "auto", "off" or "ctas,warps,rows" (MSV_CUDA_FAST_CTAS)')
     args = ap.parse_args()
 
@@ -78,9 +78,7 @@ def main() -> None:
                 os.environ.pop("MSV_CUDA_BULK_SLOTS", None)
             os.environ.pop("MSV_CUDA_FAST_CTAS", None)
             os.environ.pop("MSV_CUDA_NO_FAST_CTAS", None)
-            if fast == "off":
-                os.environ["MSV_CUDA_NO_FAST_CTAS"] = "1"
-            elif fast != "auto":
+            if fast != "off":
                 os.environ["MSV_CUDA_FAST_CTAS"] = fast
             for _ in range(2):
                 db.score_device(model, scores, stream.cuda_stream)
