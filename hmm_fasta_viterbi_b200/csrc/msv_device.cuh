@@ -41,17 +41,16 @@ struct Scan_params {
 // everything else (3000 rows at ~530 clocks per row against ~0.5 ms for the whole scan of 100 k sequences).  Cutting the slot
 // count of EVERY CTA (what the planner did before) trades throughput for it everywhere; instead a few "fast" CTAs run with
 // a fraction of the threads, take the long sequences first (tickets [0, n_long)) and carry on with the rest, while the full
-// CTAs work through tickets [n_long, n) and only help with long ones when nothing else is left.
+// CTAs work through tickets [n_long, n) only.
 __device__ __forceinline__ uint32_t next_ticket(const Scan_params& p, const bool fast_cta) {
     if (p.n_long == 0) return atomicAdd(p.queue_head, 1u);
     if (fast_cta) {
         const uint32_t t = atomicAdd(p.queue_head, 1u);
         if (t < p.n_long) return t;
     }
-    const uint32_t t = p.n_long + atomicAdd(p.queue_head + 1, 1u);
-    if (t < p.n || fast_cta) return t;
-    const uint32_t late = atomicAdd(p.queue_head, 1u);
-    return late < p.n_long ? late : p.n;
+    // (a full CTA never takes a long sequence, not even when nothing else is left: started late on a slow slot it would
+    // finish long after the fast CTAs have dealt with the rest)
+    return p.n_long + atomicAdd(p.queue_head + 1, 1u);
 }
 
 // the one store per sequence: local result plus, for the fused gather, the same 4 bytes into every peer's array

@@ -47,6 +47,8 @@ def main() -> None:
     else:
         packed = msv.Packed_sequences.synthetic_swissprot_like(args.sequences, 20261018)
     codes, offsets = packed.residues, packed.offsets
+    if any(f != "off" for f in args.fast):
+        os.environ["MSV_CUDA_FAST_CTAS"] = "auto"  # the database keeps its length profile only when the experiment is on
     db = msv.Database(codes, offsets)
     cells = leng * float(offsets[-1])
     scores = torch.empty(len(packed), dtype=torch.float32, device="cuda")
