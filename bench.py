@@ -707,7 +707,7 @@ def main() -> None:
     fence()
 
     # ---- side keys for N > 1 ----
-    nccl_gather = weak = None
+    nccl_gather = weak = gather_forms = None
     if world > 1 and not args.no_side_keys:
         side_steps = max(3, min(args.steps, 10))
         if fused is not None:  # plain scan + NCCL all-gather of padded slices; must be the same bits as the fused gather
@@ -730,6 +730,47 @@ def main() -> None:
             flags = torch.tensor([n0.elapsed_time(n1) / side_steps, 0.0 if same else 1.0], dtype=torch.float64, device="cuda")
             dist.all_reduce(flags, op=dist.ReduceOp.MAX)
             nccl_gather = {"ms_per_step": float(flags[0].item()), "same_bits_as_fused_gather_on_every_rank": float(flags[1].item()) == 0.0}
+        if fused is not None:
+            # the two forms of the gather (launch_scan in msv_cuda.cu) and their pieces, device-timed, max over ranks; every
+            # measurement is bracketed by a fence so that all ranks start together
+            def timed_piece(fn) -> float:
+                for _ in range(3):
+                    fn()
+                fence()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(side_steps):
+                    fn()
+                b.record(stream)
+                fence()
+                v = torch.tensor([a.elapsed_time(b) / side_steps], dtype=torch.float64, device="cuda")
+                dist.all_reduce(v, op=dist.ReduceOp.MAX)
+                return round(float(v.item()), 4)
+
+            gather_forms = {"unit": "ms per step, max over ranks", "default": os.environ.get("MSV_CUDA_GATHER", "library default")}
+            previous = os.environ.get("MSV_CUDA_GATHER")
+            for form in ("stores", "push"):
+                os.environ["MSV_CUDA_GATHER"] = form
+                gather_forms[form] = {
+                    "scan_and_barrier": timed_piece(lambda: fused.scan(model, db, stream.cuda_stream)),
+                    "scan_without_barrier": timed_piece(lambda: db.score_gather(model, fused._copies, fused.first_index, stream.cuda_stream)),
+                }
+                fused.scores.fill_(float("nan"))
+                fence()
+                fused.scan(model, db, stream.cuda_stream)
+                fence()
+                mine_ok = torch.equal(fused.scores[int(bounds[rank]) if strong else rank * fused.slot:][:n_local].view(torch.int32),
+                                      scores[:n_local].view(torch.int32))
+                whole_ok = not bool(torch.isnan(fused.scores[:n_total] if strong else fused.scores).any().item()) if strong else True
+                ok = torch.tensor([1.0 if (mine_ok and whole_ok) else 0.0], device="cuda")
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                gather_forms[form]["every_rank_holds_the_whole_job"] = float(ok.item()) == 1.0
+            if previous is None:
+                os.environ.pop("MSV_CUDA_GATHER", None)
+            else:
+                os.environ["MSV_CUDA_GATHER"] = previous
+            gather_forms["barrier_alone"] = timed_piece(lambda: fused._handle.barrier(channel=0))
+            gather_forms["plain_scan"] = timed_piece(lambda: db.score_device(model, scores, stream.cuda_stream))
         if strong:  # weak scaling next to it: every rank scans a whole 1M-sequence database of its own
             own = msv.Packed_sequences.synthetic_swissprot_like(args.sequences, SEED + rank)
             own_db = msv.Database(own.residues, own.offsets, device=local)
@@ -843,6 +884,8 @@ def main() -> None:
                 ms_nccl = nccl_gather.pop("ms_per_step")
                 out["nccl_gather"] = {"value": cells_job / (ms_nccl / 1e3) / 1e9, "unit": "GCUPS", "ms_per_step": ms_nccl,
                                       "what": "plain scan + NCCL all_gather_into_tensor"} | nccl_gather
+            if gather_forms is not None:
+                out["gather_forms"] = gather_forms
             if weak is not None:
                 out["weak_scaling"] = weak
             if single_process is not None:

@@ -57,7 +57,11 @@ struct Geometry {
     Scan_kernel fn_cj_same_blocks = nullptr; // warp family: speculation in checkpointed blocks (fn_cj_same speculates on whole sequences)
     Scan_kernel fn_group_spec = nullptr;    // lane-group family (G = 8): speculative scan; failures go to a second, exact launch
     // (four lanes per sequence: two interleaved copies of the table, see msv_scan_kernel)
-    size_t shared_bytes() const { return static_cast<size_t>(MSV_ALPHABET) * (K - std::max(KT, 0)) * std::max(G, KT < 0 ? 8 : G) * sizeof(float); }
+    // lane-group family with K % 4 == 2: the two highest columns of a lane are a pair behind the quads, 128 bytes per residue
+    size_t shared_bytes() const {
+        if (KT < 0) return static_cast<size_t>(MSV_ALPHABET) * (static_cast<size_t>(K / 4) * std::max(G, 8) * 16 + (K % 4 ? 128 : 0));
+        return static_cast<size_t>(MSV_ALPHABET) * (K - KT) * G * sizeof(float);
+    }
 };
 
 // speculative lane-group scan: ahead of the exact one by 15 % at K = 16 (LENG 100) and 2 % at K = 28, behind it from K = 40 up
@@ -130,7 +134,11 @@ const Geometry g_geometries[] = {generic_entry<32, 44>(), warp_entry_ahead<44, 2
 #else
 #define MSV_FOR_EACH_K_TO_56(X, A)                                                                                     \
     X(A, 4) X(A, 8) X(A, 12) X(A, 16) X(A, 20) X(A, 24) X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56)
+// lane groups with K % 4 == 2 (less padding for the short models; G = 4 and 8 only)
+#define MSV_FOR_EACH_K_PAIR(X, A)                                                                                      \
+    X(A, 6) X(A, 10) X(A, 14) X(A, 18) X(A, 22) X(A, 26) X(A, 30) X(A, 34) X(A, 38) X(A, 42) X(A, 46) X(A, 50) X(A, 54)
 const Geometry g_geometries[] = {MSV_FOR_EACH_K_TO_56(MSV_GENERIC, 4) MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(MSV_GENERIC, 16) MSV_FOR_EACH_K(MSV_GENERIC, 32)
+                                     MSV_FOR_EACH_K_PAIR(MSV_GENERIC, 4) MSV_FOR_EACH_K_PAIR(MSV_GENERIC, 8)
                                      MSV_WARP(0, 4) MSV_WARP(0, 8) MSV_WARP(8, 8) MSV_WARP(8, 12) MSV_WARP(8, 16) MSV_WARP(8, 20)
                                          MSV_WARP(16, 16) MSV_WARP(16, 20) MSV_WARP(24, 24) MSV_FOR_EACH_K_FROM_24(MSV_WARP, 16)
                                              MSV_FOR_EACH_K_FROM_28(MSV_WARP, 24) MSV_WARP(0, 44) MSV_WARP(8, 44)
@@ -204,13 +212,13 @@ const Geometry* choose_geometry(size_t columns) {
 // (profiles/r01/sweep_generic_v3.jsonl) it beats the warp plan for LENG 200-447 when there are enough sequences to
 // balance its four times more slots (plan_launch checks that per launch).
 const Geometry* choose_octet_geometry(size_t columns) {
-    const int K = std::max(4, round_up4((columns + 1 + 7) / 8)); // 8*K > columns
+    const int K = std::max(4, static_cast<int>((columns + 1 + 7) / 8 + 1) / 2 * 2); // 8*K > columns, K even
     return (columns >= 64 && K <= 56) ? find_geometry(8, K, -1) : nullptr;
 }
 // Four lanes per sequence (eight sequences per warp) for the shortest models: less padding (LENG 100: 112 instead of 128
 // slots) and the per-row bookkeeping of a warp is shared by eight sequences.
 const Geometry* choose_narrow_geometry(size_t columns) {
-    const int K = std::max(4, round_up4((columns + 1 + 3) / 4)); // 4*K > columns
+    const int K = std::max(4, static_cast<int>((columns + 1 + 3) / 4 + 1) / 2 * 2); // 4*K > columns, K even
     return (columns >= 32 && K <= 56) ? find_geometry(4, K, -1) : nullptr;
 }
 
@@ -653,6 +661,8 @@ Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, 
     return best;
 }
 
+constexpr bool kGatherPushByDefault = false; // see launch_scan
+
 // One launch of the scan over sequences [first, first+count) of `db`; scores go to d_scores[first ..).
 Length_profile whole_profile(const msv_db* db) { // of the whole database, when its offsets passed through the host
     if (db->h_profile_count.size() != kProfileBuckets) return {};
@@ -680,8 +690,26 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     p.tr_B_Mk = model->tr_B_Mk;
     p.tr_E_C = model->tr_E_C;
     p.tr_E_J = model->tr_E_J;
-    p.n_mirrors = static_cast<uint32_t>(n_mirrors);
+    // Gather of a sharded run (mirrors = the peers' copies of the job's score array).  Two forms, same result:
+    //   stores : every score is stored into all copies by the lane that computed it (store_score) -- no second kernel, the
+    //            transfer rides along with the scan; n_mirrors remote 4-byte stores per sequence;
+    //   push   : the scan writes this GPU's copy only, and a small kernel behind it copies the slice into the peers' copies
+    //            with coalesced stores (score_push_kernel).
+    // MSV_CUDA_GATHER=stores|push overrides the default.
+    const char* gather_env = std::getenv("MSV_CUDA_GATHER");
+    const bool push = n_mirrors > 0 && (gather_env ? std::strcmp(gather_env, "push") == 0 : kGatherPushByDefault);
+    p.n_mirrors = push ? 0u : static_cast<uint32_t>(n_mirrors);
     for (int r = 0; r < n_mirrors; ++r) p.mirrors[r] = mirrors[r] + first;
+    const auto push_slice = [&]() -> int { // this launch's slice is contiguous: sequences [first, first + count)
+        if (!push) return MSV_OK;
+        msv::Score_mirrors peers{};
+        for (int r = 0; r < n_mirrors; ++r) peers.copy[r] = mirrors[r] + first;
+        const int blocks = static_cast<int>(std::min<size_t>(static_cast<size_t>(model->sm_count), (count + 1023) / 1024));
+        msv::score_push_kernel<<<blocks, 256, 0, stream>>>(d_scores + first, peers, static_cast<uint32_t>(n_mirrors), count);
+        ++g_launches;
+        MSV_CUDA_TRY(cudaGetLastError());
+        return MSV_OK;
+    };
     MSV_CUDA_TRY(cudaMemsetAsync(db->d_queue + 2 * queue_slot, 0, 2 * sizeof(unsigned int), stream));
     // persistent CTAs, at most one per SM; a "slot" scans one sequence at a time (lane group, warp or four warps)
     const size_t threads_per_slot = static_cast<size_t>(geo->G);
@@ -703,7 +731,7 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
         geo->fn_group_spec<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
         ++g_launches;
         MSV_CUDA_TRY(cudaGetLastError());
-        return MSV_OK;
+        return push_slice();
     }
     Scan_kernel kernel = cj_same ? geo->fn_cj_same : geo->fn;
     // Two speculating warp kernels (msv_kernels.cuh).  fn_cj_same speculates on a whole sequence (up to 4096 rows) and scans
@@ -733,6 +761,7 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
     kernel<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
     ++g_launches;
     MSV_CUDA_TRY(cudaGetLastError());
+    if (int rc = push_slice()) return rc;
     if (feedback)
         MSV_CUDA_TRY(cudaMemcpyAsync(const_cast<unsigned int*>(model->h_speculation_totals), model->d_speculation_totals,
                                      2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
@@ -1153,7 +1182,9 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         const int G = geo->G, K = geo->K, KT = std::max(geo->KT, 0), KS = K - KT;
         const int copies = (geo->KT < 0 && G < 8) ? 8 / G : 1; // lane groups narrower than a quarter-warp: interleaved copies
         const int R = G * copies;                               // lane slots per quad row of the shared-memory table
-        const size_t shared_floats = static_cast<size_t>(MSV_ALPHABET) * KS * R;
+        const bool pair = geo->KT < 0 && KS % 4 == 2; // lane groups: the two highest columns, 16 lane slots x 2 floats behind the quads
+        const size_t row_floats = static_cast<size_t>(KS / 4) * R * 4 + (pair ? 32 : 0);
+        const size_t shared_floats = static_cast<size_t>(MSV_ALPHABET) * row_floats;
         const size_t floats = shared_floats + static_cast<size_t>(MSV_ALPHABET) * KT * G;
         std::vector<float> laid(std::max<size_t>(floats, 4), -std::numeric_limits<float>::infinity());
         const auto emission = [&](int res, int g, int j) {
@@ -1164,9 +1195,13 @@ int msv_cuda_model_create(const float* emission_scores, size_t model_length, flo
         const int shared_first = tensor_high ? 0 : KT, tensor_first = tensor_high ? KS : 0;
         for (int res = 0; res < MSV_ALPHABET; ++res)
             for (int g = 0; g < G; ++g) {
-                for (int js = 0; js < KS; ++js)
+                for (int js = 0; js < KS / 4 * 4; ++js)
                     for (int copy = 0; copy < copies; ++copy)
-                        laid[((static_cast<size_t>(res) * (KS / 4) + js / 4) * R + copy * G + g) * 4 + js % 4] = emission(res, g, shared_first + js);
+                        laid[res * row_floats + (static_cast<size_t>(js / 4) * R + copy * G + g) * 4 + js % 4] = emission(res, g, shared_first + js);
+                if (pair)
+                    for (int copy = 0; copy < 16 / G; ++copy)
+                        for (int jp = 0; jp < 2; ++jp)
+                            laid[res * row_floats + static_cast<size_t>(KS / 4) * R * 4 + (copy * G + g) * 2 + jp] = emission(res, g, KS / 4 * 4 + jp);
                 for (int jt = 0; jt < KT; ++jt)
                     laid[shared_floats + (static_cast<size_t>(res) * G + g) * KT + jt] = emission(res, g, tensor_first + jt);
             }

@@ -114,6 +114,12 @@ __device__ __forceinline__ float4 lds128(uint32_t shared_address) {
     return v;
 }
 
+__device__ __forceinline__ float2 lds64(uint32_t shared_address) {
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(shared_address));
+    return v;
+}
+
 // same, but never hoisted out of a loop or merged: for loop-invariant tables that must NOT be promoted to registers
 __device__ __forceinline__ float4 lds128_volatile(uint32_t shared_address) {
     float4 v;

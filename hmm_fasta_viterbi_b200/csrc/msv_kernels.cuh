@@ -51,10 +51,16 @@ namespace msv {
 template <int G, int K, int THREADS, bool CJ_SAME>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params p) {
     static_assert(G == 4 || G == 8 || G == 16 || G == 32, "lanes per sequence");
-    static_assert(K % 4 == 0 && K >= 4 && K <= kMaxColumnsPerLane, "columns per lane");
+    static_assert(K % 2 == 0 && (K % 4 == 0 || G <= 8) && K >= 4 && K <= kMaxColumnsPerLane, "columns per lane");
     constexpr int LANES_PER_QUAD_ROW = G < 8 ? 8 : G;
     constexpr uint32_t QUAD_BYTES = LANES_PER_QUAD_ROW * 16;
-    constexpr uint32_t ROW_BYTES = (K / 4) * QUAD_BYTES; // bytes per residue row of the table
+    // K % 4 == 2 (G = 4, 8: less padding, e.g. 4 x 26 = 104 slots for LENG 100 instead of 112): the two highest columns of
+    // every lane are a PAIR stored behind the quads of the residue row, 128 bytes = 16 lane slots x 8 bytes, read with one
+    // LDS.64.  An LDS.64 is served per half-warp, which holds 16 / G groups with different residues, so the pair is stored
+    // 16 / G times side by side and lane l reads slot l % 16: every half-warp touches each bank once, whatever the residues.
+    constexpr bool PAIR = K % 4 == 2;
+    constexpr uint32_t PAIR_OFFSET = (K / 4) * QUAD_BYTES;
+    constexpr uint32_t ROW_BYTES = PAIR_OFFSET + (PAIR ? 128u : 0u); // bytes per residue row of the table
     constexpr uint32_t COPY_CHUNK = 32768;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -82,6 +88,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
     const int left_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1)); // rotate inside the group
     const uint32_t tab_lane = smem_u32(smem_raw) + (lane & (LANES_PER_QUAD_ROW - 1)) * 16;
+    [[maybe_unused]] const uint32_t pair_lane = smem_u32(smem_raw) + PAIR_OFFSET + (lane & 15) * 8;
     const float NEG_INF = __int_as_float(0xff800000);
     const float tBMk = p.tr_B_Mk, tEC = p.tr_E_C, tEJ = p.tr_E_J;
 
@@ -143,6 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
 #pragma unroll 1
         for (uint32_t t = 0; t < steps; ++t) {
             const uint32_t erow = tab_lane + (buf & 0xffu) * ROW_BYTES;
+            [[maybe_unused]] const uint32_t prow = pair_lane + (buf & 0xffu) * ROW_BYTES;
             buf >>= 8;
             if (--have == 0) {
                 buf = nextw;
@@ -154,6 +162,12 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
             const float left = __shfl_sync(0xffffffffu, m[K - 1], left_lane);
 
             float e = NEG_INF;
+            if constexpr (PAIR) { // the two highest columns first (every cell reads its not-yet-overwritten left neighbour)
+                const float2 ev = lds64(prow);
+                m[K - 1] = ev.y + fmaxf(m[K - 2], bt);
+                m[K - 2] = ev.x + fmaxf(m[K - 3], bt);
+                e = fmaxf(m[K - 1], m[K - 2]);
+            }
 #pragma unroll
             for (int q = K / 4 - 1; q >= 0; --q) {
                 const float4 ev = lds128(erow + q * QUAD_BYTES);
@@ -189,10 +203,12 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_kernel(const Scan_params 
 template <int G, int K, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const Scan_params p) {
     static_assert(G == 4 || G == 8 || G == 16, "lanes per sequence");
-    static_assert(K % 4 == 0 && K >= 4 && K <= kMaxColumnsPerLane, "columns per lane");
+    static_assert(K % 2 == 0 && (K % 4 == 0 || G <= 8) && K >= 4 && K <= kMaxColumnsPerLane, "columns per lane");
     constexpr int LANES_PER_QUAD_ROW = G < 8 ? 8 : G; // G = 4: two copies of the table side by side, one per neighbouring group
     constexpr uint32_t QUAD_BYTES = LANES_PER_QUAD_ROW * 16;
-    constexpr uint32_t ROW_BYTES = (K / 4) * QUAD_BYTES;
+    constexpr bool PAIR = K % 4 == 2; // the two highest columns of a lane: one LDS.64 from 16 lane slots behind the quads (msv_scan_kernel)
+    constexpr uint32_t PAIR_OFFSET = (K / 4) * QUAD_BYTES;
+    constexpr uint32_t ROW_BYTES = PAIR_OFFSET + (PAIR ? 128u : 0u);
     constexpr uint32_t COPY_CHUNK = 32768;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -218,6 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
     const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
     const int left_lane = (lane & ~(G - 1)) | ((gl + G - 1) & (G - 1)); // rotate inside the group
     const uint32_t tab_lane = smem_u32(smem_raw) + (lane & (LANES_PER_QUAD_ROW - 1)) * 16;
+    [[maybe_unused]] const uint32_t pair_lane = smem_u32(smem_raw) + PAIR_OFFSET + (lane & 15) * 8;
     const float NEG_INF = __int_as_float(0xff800000);
     const float tBMk = p.tr_B_Mk, tEJ = p.tr_E_J;
 
@@ -238,6 +255,12 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_group_spec_kernel(const S
         const float bt = B + tBMk;
         const float left = __shfl_sync(0xffffffffu, m[K - 1], left_lane);
         e = NEG_INF;
+        if constexpr (PAIR) {
+            const float2 ev = lds64(pair_lane + x * ROW_BYTES);
+            m[K - 1] = ev.y + fmaxf(m[K - 2], bt);
+            m[K - 2] = ev.x + fmaxf(m[K - 3], bt);
+            e = fmaxf(m[K - 1], m[K - 2]);
+        }
 #pragma unroll
         for (int q = K / 4 - 1; q >= 0; --q) {
             const float4 ev = lds128(erow + q * QUAD_BYTES);
@@ -953,6 +976,20 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_quad_kernel(const Scan_pa
         __syncthreads();
         if (warp == 0)
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_slot), "n"(TMEM_COLUMNS) : "memory");
+    }
+}
+
+// ---- gather of a sharded run, "push" form: after the scan, this GPU's slice of the job's score array (its own copy) is
+// written into every peer's copy with coalesced stores over NVLink (128 bytes per warp instruction and peer).  The other
+// form stores each score into all copies from the scan kernel itself (store_score); see launch_scan for which is used when.
+struct Score_mirrors {
+    float* copy[kMaxScoreMirrors];
+};
+__global__ void score_push_kernel(const float* __restrict__ own, const Score_mirrors peers, uint32_t n_peers, uint64_t n) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = own[i];
+        for (uint32_t r = 0; r < n_peers; ++r) peers.copy[r][i] = v;
     }
 }
 

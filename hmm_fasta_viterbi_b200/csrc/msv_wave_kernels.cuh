@@ -111,11 +111,6 @@ __device__ __forceinline__ uint4 lds128_volatile_u32(uint32_t shared_address) {
 __device__ __forceinline__ void sts128_u32(uint32_t shared_address, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(shared_address), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ float2 lds64(uint32_t shared_address) {
-    float2 v;
-    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(shared_address));
-    return v;
-}
 // float -> unsigned that orders like the float (for atomicMax); 0 is below every float, including -inf
 __device__ __forceinline__ unsigned int ordered_bits(float v) {
     const unsigned int b = __float_as_uint(v);

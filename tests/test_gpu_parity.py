@@ -99,6 +99,8 @@ def test_homologous_sequences_exercise_the_J_state(oracle):
 
 @pytest.mark.parametrize("geometry", ["4,8", "4,28", "4,52", "8,4", "8,16", "8,64", "16,8", "16,32", "16,88", "32,4", "32,20", "32,24", "32,44",
                                        "32,56", "32,60", "32,88",
+                                       # lane groups whose two highest columns are a pair read with LDS.64 (K % 4 == 2)
+                                       "4,6", "4,26", "4,38", "4,54", "8,6", "8,14", "8,26", "8,38", "8,54",
                                        # warp kernels: shared memory + KT tensor-memory columns per lane
                                        "32,4,0", "32,8,0", "32,8,8", "32,20,8", "32,24,16", "32,28,16", "32,44,0", "32,44,8",
                                        "32,44,16", "32,44,24", "32,44,16,640", "32,64,16", "32,76,16", "32,76,24", "32,88,16",
@@ -751,7 +753,8 @@ def test_speculation_falls_back_exactly_on_hits(oracle, name, monkeypatch):
         assert not model.speculation["blocks_next"], model.speculation
 
 
-@pytest.mark.parametrize("name,geometry", [("100.hmm", "8,16"), ("200.hmm", "8,28"), ("100.hmm", "4,28"), ("200.hmm", "4,52")])
+@pytest.mark.parametrize("name,geometry", [("100.hmm", "8,16"), ("200.hmm", "8,28"), ("100.hmm", "4,28"), ("200.hmm", "4,52"),
+                                           ("100.hmm", "4,26"), ("100.hmm", "8,14"), ("200.hmm", "8,26")])
 def test_group_speculation_and_its_exact_pass(oracle, name, geometry, monkeypatch):
     """Eight / four lanes per sequence, speculative rows: a sequence whose speculation fails (consensus-derived hits) is
     scanned again at once, exactly, by the same lane group inside the same launch; while it is, the other groups of its warp
