@@ -90,6 +90,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int) -> None:
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.recording = False
         self._stop_flag = threading.Event()
         try:
             import pynvml
@@ -113,11 +114,13 @@ class ClockSampler(threading.Thread):
         }
         while not self._stop_flag.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                for name, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
+                if self.recording:  # only what falls into the timed region counts
+                    self.samples.append(mhz)
+                    for name, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.01)
@@ -646,19 +649,28 @@ def main() -> None:
     # --warmup is honoured exactly; N > 1 runs SETTLE_STEPS uncounted steps first (the first ~0.3 s after communicator /
     # symmetric-memory set-up run about 1 % slow), and at least 3 steps precede the timed region in any case
     settle = (SETTLE_STEPS if world > 1 else 0) + max(0, 3 - args.warmup)
+    # (NVML is initialised and the polling thread started BEFORE the fence: nvmlInit takes tens of milliseconds when eight
+    # processes do it at once, and done between the fence and the first step it let the ranks enter the timed region that far
+    # apart -- every rank then waited for the slowest one at the first barrier, inside its timed region: 6.5 and 7.5 ms per
+    # step at 8 GPUs for a step that takes 6.08 ms, profiles/r02/bench_l_n8_strong.json, bench_n_n8_strong.json)
+    sampler = ClockSampler(local)
+    if os.environ.get("MSV_BENCH_NO_CLOCK_SAMPLER"):  # diagnostic only
+        sampler.nv = None
+    sampler.start()
     for _ in range(settle + args.warmup):
         step()
     fence()
 
     # ---- value: device-resident scan (+ gather), CUDA events ----
-    sampler = ClockSampler(local)
-    sampler.start()
     _cabi.launch_count(reset=True)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.recording = True
     start.record(stream)
     for _ in range(args.steps):
         step()
     stop.record(stream)
+    torch.cuda.synchronize()
+    sampler.recording = False
     fence()
     launches = _cabi.launch_count()
     clocks = sampler.stop()
