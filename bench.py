@@ -91,6 +91,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self.recording = False
+        self.last = None  # the most recent sample, inside the timed region or not (a very short region may see none)
         self._stop_flag = threading.Event()
         try:
             import pynvml
@@ -116,6 +117,7 @@ class ClockSampler(threading.Thread):
             try:
                 mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.last = mhz
                 if self.recording:  # only what falls into the timed region counts
                     self.samples.append(mhz)
                     for name, bit in names.items():
@@ -128,7 +130,7 @@ class ClockSampler(threading.Thread):
     def stop(self) -> dict:
         self._stop_flag.set()
         self.join(timeout=2)
-        med = float(np.median(self.samples)) if self.samples else None
+        med = float(np.median(self.samples)) if self.samples else (float(self.last) if self.last is not None else None)
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 

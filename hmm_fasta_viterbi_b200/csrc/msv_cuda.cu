@@ -64,10 +64,12 @@ struct Geometry {
     }
 };
 
-// speculative lane-group scan: ahead of the exact one by 15 % at K = 16 (LENG 100) and 2 % at K = 28, behind it from K = 40 up
-// (profiles/r01/sweep_group_spec.txt), so it exists for the short models only
+// speculative lane-group scan.  Round 1 (failed speculations went to a second launch): ahead of the exact one by 15 % at
+// K = 16 and behind it from K = 40 up.  With the exact redo inside the kernel (round 2) it is ahead everywhere the lane-group
+// plans are used: 300.hmm (8 x 38) 6.53 -> 8.13 TCUPS, 400.hmm (8 x 52) 7.00 -> 8.16 on 100 k sequences
+// (profiles/r02/group_spec_sweep_v1.txt); beyond K = 56 the warp-per-sequence kernel wins anyway (group_spec_sweep_v2.txt)
 template <int G, int K> constexpr Scan_kernel group_spec_kernel() {
-    if constexpr ((G == 8 && K <= 28) || G == 4) return msv::msv_scan_group_spec_kernel<G, K, threads_for(K)>;
+    if constexpr ((G == 8 && K <= 56) || G == 4) return msv::msv_scan_group_spec_kernel<G, K, threads_for(K)>;
     else return nullptr;
 }
 template <int G, int K> constexpr Geometry generic_entry() {

@@ -754,7 +754,8 @@ def test_speculation_falls_back_exactly_on_hits(oracle, name, monkeypatch):
 
 
 @pytest.mark.parametrize("name,geometry", [("100.hmm", "8,16"), ("200.hmm", "8,28"), ("100.hmm", "4,28"), ("200.hmm", "4,52"),
-                                           ("100.hmm", "4,26"), ("100.hmm", "8,14"), ("200.hmm", "8,26")])
+                                           ("100.hmm", "4,26"), ("100.hmm", "8,14"), ("200.hmm", "8,26"), ("300.hmm", "8,38"),
+                                           ("400.hmm", "8,52")])
 def test_group_speculation_and_its_exact_pass(oracle, name, geometry, monkeypatch):
     """Eight / four lanes per sequence, speculative rows: a sequence whose speculation fails (consensus-derived hits) is
     scanned again at once, exactly, by the same lane group inside the same launch; while it is, the other groups of its warp
