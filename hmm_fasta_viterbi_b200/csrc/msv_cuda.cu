@@ -330,6 +330,8 @@ int db_release(msv_db* db) {
     if (db->copy_stream) {
         cudaStreamDestroy(db->copy_stream);
         cudaStreamDestroy(db->compute_stream);
+        cudaStreamDestroy(db->compute_stream2);
+        cudaEventDestroy(db->other_done);
         for (auto ev : db->stage_copied) cudaEventDestroy(ev);
         cudaEventDestroy(db->reserved);
     }
@@ -383,7 +385,7 @@ int db_reserve(msv_db* db, uint64_t total, size_t n, uint64_t longest, cudaStrea
         db->cap_n = cap;
     }
     if (!db->d_hist) {
-        MSV_CUDA_TRY(cudaMalloc(&db->d_hist, 2 * kBuckets * sizeof(uint32_t)));
+        MSV_CUDA_TRY(cudaMalloc(&db->d_hist, 4 * kBuckets * sizeof(uint32_t)));
         MSV_CUDA_TRY(cudaMalloc(&db->d_queue, 2 * kMaxChunks * sizeof(unsigned int))); // per upload stage: queue head, head of its second part (next_ticket)
         MSV_CUDA_TRY(cudaMalloc(&db->d_first_bad, sizeof(unsigned long long)));
     }
@@ -414,7 +416,8 @@ int db_reserve(msv_db* db, uint64_t total, size_t n, uint64_t longest, cudaStrea
 // Validate the residue codes of sequences [first, first+count) and bucket them longest-first into
 // d_order[first .. first+count) (indices relative to `first`).  Everything is queued on `stream`.
 int db_prepare_range(msv_db* db, size_t first, size_t count, uint64_t residue_begin, uint64_t residue_end, uint64_t longest,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int scratch = 0) {
+    uint32_t* const d_hist = db->d_hist + static_cast<size_t>(scratch) * 2 * kBuckets; // hist | cursor of this stream
     if (count == 0) return MSV_OK;
     if (residue_end > residue_begin) {
         // 16-byte words that cover the range; neighbouring ranges may be checked twice, which is harmless
@@ -432,12 +435,12 @@ int db_prepare_range(msv_db* db, size_t first, size_t count, uint64_t residue_be
     uint32_t shift = 0;
     while ((longest >> shift) >= kBuckets) ++shift;
     const uint32_t used_buckets = static_cast<uint32_t>(std::min<uint64_t>((longest >> shift) + 1, kBuckets));
-    MSV_CUDA_TRY(cudaMemsetAsync(db->d_hist, 0, used_buckets * sizeof(uint32_t), stream));
+    MSV_CUDA_TRY(cudaMemsetAsync(d_hist, 0, used_buckets * sizeof(uint32_t), stream));
     const uint32_t n32 = static_cast<uint32_t>(count);
     const int blocks_n = static_cast<int>((count + 255) / 256);
-    msv::db_histogram_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets + first, n32, shift, used_buckets, db->d_hist);
-    msv::db_scan_kernel<<<1, 1024, 0, stream>>>(db->d_hist, used_buckets, db->d_hist + kBuckets);
-    msv::db_scatter_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets + first, n32, shift, used_buckets, db->d_hist + kBuckets,
+    msv::db_histogram_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets + first, n32, shift, used_buckets, d_hist);
+    msv::db_scan_kernel<<<1, 1024, 0, stream>>>(d_hist, used_buckets, d_hist + kBuckets);
+    msv::db_scatter_kernel<<<blocks_n, 256, 0, stream>>>(db->d_offsets + first, n32, shift, used_buckets, d_hist + kBuckets,
                                                          db->d_order + first);
     g_launches += 3;
     MSV_CUDA_TRY(cudaGetLastError());
@@ -781,13 +784,21 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
     if (!db->copy_stream) {
         MSV_CUDA_TRY(cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking));
         MSV_CUDA_TRY(cudaStreamCreateWithFlags(&db->compute_stream, cudaStreamNonBlocking));
+        MSV_CUDA_TRY(cudaStreamCreateWithFlags(&db->compute_stream2, cudaStreamNonBlocking));
         for (auto& ev : db->stage_copied) MSV_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         MSV_CUDA_TRY(cudaEventCreateWithFlags(&db->reserved, cudaEventDisableTiming));
+        MSV_CUDA_TRY(cudaEventCreateWithFlags(&db->other_done, cudaEventDisableTiming));
     }
     cudaStream_t copy = db->copy_stream, compute = db->compute_stream;
+    // Stages alternate between two compute streams: the persistent scan kernel of a stage ends with a tail in which most SMs
+    // are already idle (every CTA waits for its last warp), and with the next stage on another stream its bucketing kernels
+    // and scan CTAs move onto those SMs as they become free instead of waiting for the last CTA of the stage before.
+    // MSV_CUDA_ONE_COMPUTE_STREAM=1 keeps everything on one stream (tuning aid).
+    cudaStream_t const lanes[2] = {compute, std::getenv("MSV_CUDA_ONE_COMPUTE_STREAM") ? compute : db->compute_stream2};
     if (int rc = db_reserve(db, total, n, longest, compute)) return rc;
     MSV_CUDA_TRY(cudaEventRecord(db->reserved, compute));
     MSV_CUDA_TRY(cudaStreamWaitEvent(copy, db->reserved, 0)); // buffers may have been reallocated
+    if (lanes[1] != compute) MSV_CUDA_TRY(cudaStreamWaitEvent(lanes[1], db->reserved, 0));
     db->n = n;
     db->total = total;
     db->longest = longest;
@@ -803,7 +814,11 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
     {
         // few sequences: one stage, so that the launch planner can balance them all at once (the upload is short anyway)
         const size_t warp_slots = static_cast<size_t>(model->sm_count) * 16;
-        uint64_t stage_bytes = 2ull << 20, cut = 0;
+        // first stage: 8 MB (~23 k sequences).  2 MB (round 1) started the scan 0.1 ms earlier, but a 6 k-sequence launch on 2368
+        // warp slots ends when its longest sequence does -- ~0.8 ms for 0.28 ms of work.  MSV_CUDA_FIRST_STAGE_MB overrides.
+        uint64_t first_mb = 8;
+        if (const char* env = std::getenv("MSV_CUDA_FIRST_STAGE_MB")) first_mb = std::max(1, std::atoi(env));
+        uint64_t stage_bytes = first_mb << 20, cut = 0;
         while (n >= 4 * warp_slots && stages < kMaxChunks - 1 && cut + stage_bytes + (stage_bytes >> 1) < total) {
             cut += stage_bytes;
             size_t q = static_cast<size_t>(std::lower_bound(offsets, offsets + n + 1, cut) - offsets);
@@ -824,17 +839,22 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
             const uint64_t begin = offsets[first], end = offsets[last];
             if (end > begin)
                 MSV_CUDA_TRY(cudaMemcpyAsync(db->d_residues + begin, residues + begin, end - begin, cudaMemcpyHostToDevice, copy));
+            cudaStream_t const lane = lanes[s & 1];
             MSV_CUDA_TRY(cudaEventRecord(db->stage_copied[s], copy));
-            MSV_CUDA_TRY(cudaStreamWaitEvent(compute, db->stage_copied[s], 0));
-            if (int rc = db_prepare_range(db, first, last - first, begin, end, longest, compute)) return rc;
+            MSV_CUDA_TRY(cudaStreamWaitEvent(lane, db->stage_copied[s], 0));
+            if (int rc = db_prepare_range(db, first, last - first, begin, end, longest, lane, s & 1)) return rc;
             Length_profile stage_profile;
             if (stages > 1 && (model->narrow.geo || model->octet.geo) && std::getenv("MSV_CUDA_FAST_CTAS")) { // (experiment, see plan_launch)
                 profile_lengths(offsets, first, last - first, stage_counts, stage_rows);
                 stage_profile = {stage_counts.data(), stage_rows.data()};
             }
-            if (int rc = launch_scan(model, db, first, last - first, end - begin, s, d_out, compute, mirrors, n_mirrors,
+            if (int rc = launch_scan(model, db, first, last - first, end - begin, s, d_out, lane, mirrors, n_mirrors,
                                      stage_profile.count ? &stage_profile : nullptr))
                 return rc;
+        }
+        if (lanes[1] != compute) { // everything the second stream did happens before the download and the verdict
+            MSV_CUDA_TRY(cudaEventRecord(db->other_done, lanes[1]));
+            MSV_CUDA_TRY(cudaStreamWaitEvent(compute, db->other_done, 0));
         }
         if (scores_host) MSV_CUDA_TRY(cudaMemcpyAsync(scores_host, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, compute));
         return db_read_validation(db, residues, compute);
@@ -846,6 +866,7 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
         const std::string message = g_last_error;
         (void)cudaStreamSynchronize(copy);
         (void)cudaStreamSynchronize(compute);
+        (void)cudaStreamSynchronize(db->compute_stream2);
         (void)cudaGetLastError();
         db->n = 0;
         g_last_error = message;

@@ -56,7 +56,7 @@ struct msv_db {
     size_t cap_n = 0;
     float2* d_length_tr = nullptr;
     size_t cap_tr = 0;
-    uint32_t* d_hist = nullptr; // hist | cursor, 2 * kBuckets
+    uint32_t* d_hist = nullptr; // hist | cursor, 2 * kBuckets; twice (the pipelined upload buckets alternate stages on two streams)
     unsigned int* d_queue = nullptr;
     unsigned long long* d_first_bad = nullptr;
     std::vector<float2> h_length_tr; // host copy, extended lazily
@@ -67,9 +67,9 @@ struct msv_db {
     std::vector<uint32_t> h_profile_count;
     std::vector<uint64_t> h_profile_rows;
     // pipelined upload (msv_cuda_score_batch): copy engine and scan overlap
-    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr, compute_stream2 = nullptr;
     cudaEvent_t stage_copied[kMaxChunks] = {};
-    cudaEvent_t reserved = nullptr;
+    cudaEvent_t reserved = nullptr, other_done = nullptr;
     // filter stages kept on the device (filter_cuda.cu): scratch + the survivors of the last MSV filter stage
     void* filter_scratch = nullptr;
     void (*filter_scratch_free)(void*) = nullptr;
