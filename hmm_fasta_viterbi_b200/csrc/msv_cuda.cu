@@ -819,12 +819,17 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
         uint64_t first_mb = 8;
         if (const char* env = std::getenv("MSV_CUDA_FIRST_STAGE_MB")) first_mb = std::max(1, std::atoi(env));
         uint64_t stage_bytes = first_mb << 20, cut = 0;
+        // every stage must be uploaded before the scan of the stage before it ends: the scan consumes ~8e12 / LENG bytes per
+        // second, the link delivers ~45e9, so a stage may be LENG / 220 times the size of its predecessor (at most 4x, at least
+        // 1.5x: short models are upload-bound whatever the stages are).  MSV_CUDA_STAGE_GROWTH overrides.
+        double growth = std::min(4.0, std::max(1.5, static_cast<double>(model->model_length - 1) / 220.0));
+        if (const char* env = std::getenv("MSV_CUDA_STAGE_GROWTH")) growth = std::max(1.1, std::atof(env));
         while (n >= 4 * warp_slots && stages < kMaxChunks - 1 && cut + stage_bytes + (stage_bytes >> 1) < total) {
             cut += stage_bytes;
             size_t q = static_cast<size_t>(std::lower_bound(offsets, offsets + n + 1, cut) - offsets);
             q = std::min(q, n);
             if (q > bounds[stages]) bounds[++stages] = q;
-            stage_bytes *= 4;
+            stage_bytes = static_cast<uint64_t>(static_cast<double>(stage_bytes) * growth);
         }
         if (bounds[stages] < n || stages == 0) bounds[++stages] = n;
     }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """End-to-end call (msv_cuda_score_batch: pinned host buffers in, host scores out) against the resident scan, for database
 sizes from one GPU's share of an 8-GPU job (125 k sequences) to the whole config-4 database, under the tuning switches of the
-pipelined upload: MSV_CUDA_FIRST_STAGE_MB and MSV_CUDA_ONE_COMPUTE_STREAM.  One JSON line per (size, setting)."""
+pipelined upload: MSV_CUDA_FIRST_STAGE_MB, MSV_CUDA_STAGE_GROWTH and MSV_CUDA_ONE_COMPUTE_STREAM.  One JSON line per (size, setting)."""
 import json
 import os
 import sys
@@ -30,8 +30,12 @@ for n in (125_000, 250_000, 1_000_000):
     for _ in range(5):
         db.score(model)
     resident_ms = (time.perf_counter() - t0) / 5 * 1e3  # includes the 4 n-byte download
-    for stage_mb, one_stream in ((2, True), (8, True), (2, False), (4, False), (8, False), (16, False)):
+    for stage_mb, one_stream, growth in ((2, True, 4), (8, True, 4), (8, False, 4), (8, False, 0), (8, False, 2), (8, False, 1.5), (4, False, 0)):
         os.environ["MSV_CUDA_FIRST_STAGE_MB"] = str(stage_mb)
+        if growth:
+            os.environ["MSV_CUDA_STAGE_GROWTH"] = str(growth)
+        else:
+            os.environ.pop("MSV_CUDA_STAGE_GROWTH", None)  # the library's own choice from the model length
         if one_stream:
             os.environ["MSV_CUDA_ONE_COMPUTE_STREAM"] = "1"
         else:
@@ -43,7 +47,7 @@ for n in (125_000, 250_000, 1_000_000):
         for _ in range(reps):
             model.score_batch(codes, offsets, out)
         ms = (time.perf_counter() - t0) / reps * 1e3
-        print(json.dumps({"model": model_name, "sequences": n, "first_stage_mb": stage_mb, "compute_streams": 1 if one_stream else 2,
+        print(json.dumps({"model": model_name, "sequences": n, "first_stage_mb": stage_mb, "compute_streams": 1 if one_stream else 2, "stage_growth": growth or "auto",
                           "e2e_ms": round(ms, 3), "e2e_gcups": round(cells / ms / 1e6, 1), "resident_scan_plus_download_ms": round(resident_ms, 3),
                           "same_bits": bool((out.view(np.uint32) == want.view(np.uint32)).all())}), flush=True)
     for a in (codes, offsets, out):
