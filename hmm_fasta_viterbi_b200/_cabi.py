@@ -255,7 +255,7 @@ class Model:
         """Running totals behind the choice of the speculating kernel (see msv_cuda.h) and what the next scan would use."""
         f, o, b = C.c_uint(), C.c_uint(), C.c_int()
         check(lib.msv_cuda_model_speculation(self.handle, C.byref(f), C.byref(o), C.byref(b)))
-        return {"failed": f.value, "offered": o.value, "blocks_next": bool(b.value)}
+        return {"failed": f.value, "scanned": o.value, "rows_next": ("exact", "whole", "blocks")[b.value]}
 
     def plan(self, database: "Database") -> dict:
         """Launch plan a scan of `database` would use: kernel family (lanes per sequence) and sequences per CTA."""

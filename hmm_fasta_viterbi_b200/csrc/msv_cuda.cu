@@ -80,7 +80,18 @@ template <int G, int K> constexpr Geometry generic_entry() {
 // ahead of the exact rows (profiles/r01/sweep_speculation*.txt: +13 % at K = 4, +2..6 % at K = 16..22 and 32..38, level at
 // K = 8..14 and 42, 44; behind by 1 % at K = 26..30 and by 5..8 % from K = 48 up, where the two row bodies no longer share
 // the instruction cache).
-constexpr bool speculation_pays(int K) { return K <= 44 && !(K >= 26 && K <= 30); }
+// The row variant of the warp kernel that is fastest on a database WITHOUT hits, per columns-per-lane K: B200 sweep over the
+// fixture models, profiles/r02/speculation_sweep_v2.txt (100 k sequences; exact / whole-sequence / block-wise speculation, e.g.
+// K = 44: 9.76 / 10.05 / 9.77 TCUPS, K = 38: 9.16 / 9.32 / 9.57, K = 42: 9.41 / 9.29 / 9.08, K = 48: 9.87 / 9.63 / 8.91).
+// It is not monotone in K -- the compiler's schedule of three different loop nests at the register limit -- and beyond
+// K = 44 the two row bodies no longer share the instruction cache.  Unmeasured K keep round 1's rule.
+enum Rows { kExact = 0, kWhole = 1, kBlocks = 2 };
+constexpr Rows quiet_rows(int K) {
+    if (K > 44 || K == 26 || K == 28 || K == 42) return kExact;
+    if (K == 16 || K == 38) return kBlocks;
+    return kWhole;
+}
+constexpr bool speculation_pays(int K) { return quiet_rows(K) != kExact; }
 template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_kernel() {
     if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD, 1>;
     else return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD>;
@@ -285,7 +296,7 @@ struct msv_model {
     unsigned int* d_speculation_totals = nullptr;
     volatile unsigned int* h_speculation_totals = nullptr;
     unsigned int seen_failures = 0, seen_offered = 0; // totals at the last decision that had enough new sequences behind it
-    bool hits_are_common = false;
+    float hit_share = 0.0f; // failed / scanned over the sequences between the last two decisions
     // single-sequence latency path (msv_wave_kernels.cuh): a chain of warps over a thread-block cluster; built when
     // tr_E_C == tr_E_J (the kernel speculates B = N + move) and the chain fits a cluster
     struct Wave {
@@ -668,6 +679,15 @@ Launch_plan plan_launch(const msv_model* model, const msv_db* db, size_t first, 
 
 constexpr bool kGatherPushByDefault = false; // see launch_scan
 
+// Row variant of the warp kernel for a launch (only where the speculating kernels exist, i.e. quiet_rows(K) != kExact).
+Rows rows_for(int K, float hit_share, bool long_sequences) {
+    const Rows quiet = quiet_rows(K);
+    const bool blocks_are_cheap = quiet == kBlocks || K < 24; // measured: block-wise speculation is at least as fast as exact rows there
+    if (long_sequences) return blocks_are_cheap ? kBlocks : kExact;
+    if (hit_share <= 0.03f) return quiet;
+    return (blocks_are_cheap && hit_share < 0.2f) ? kBlocks : kExact;
+}
+
 // One launch of the scan over sequences [first, first+count) of `db`; scores go to d_scores[first ..).
 Length_profile whole_profile(const msv_db* db) { // of the whole database, when its offsets passed through the host
     if (db->h_profile_count.size() != kProfileBuckets) return {};
@@ -739,11 +759,14 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
         return push_slice();
     }
     Scan_kernel kernel = cj_same ? geo->fn_cj_same : geo->fn;
-    // Two speculating warp kernels (msv_kernels.cuh).  fn_cj_same speculates on a whole sequence (up to 4096 rows) and scans
-    // it again when the vote at its end fails: the faster loop (10.08 vs 9.85 TCUPS at 1400 columns), a whole extra pass per
-    // hit.  fn_cj_same_blocks checkpoints every 64 rows: a hit costs one block whatever the sequence length.  Break-even is
-    // near 2 % of the sequences failing (1 + 1.4 f = 1.023 + 0.25 f), so: blocks for long sequences (they would not
-    // speculate at all otherwise) and when the previous scans with this model saw hits that often.
+    // Three row variants of the warp kernel (msv_kernels.cuh), same bits: exact rows; speculation on whole sequences (vote at
+    // the end, a failed sequence is scanned again: one extra pass per hit, T = W / (1 + 1.09 f) for a share f of failing
+    // sequences); speculation in checkpointed blocks of 64 rows (a hit costs one block: T = B / (1 + 0.25 f)).  Which is
+    // fastest depends on K (quiet_rows) and on f (profiles/r02/hit_rate_modes_v1.jsonl, 1400.hmm at f = 0 / 0.02 / 0.1 / 0.5:
+    // whole 10.07 / 9.85 / 9.08 / 6.53, blocks 9.80 / 9.75 / 9.56 / 8.73, exact 9.78 throughout).  Every variant counts the
+    // sequences that fail (or would fail) the vote; the totals travel to pinned host memory after each launch and the next
+    // launch reads them without waiting: a database that turns out hit-rich gets exact rows from the second scan on (blocks
+    // where blocks are the fastest variant anyway and hits are not the majority), long sequences never speculate as a whole.
     // MSV_CUDA_SPECULATION=whole|blocks|none overrides (tuning aid; MSV_CUDA_NO_SPECULATION is the older spelling of none).
     bool feedback = false;
     if (cj_same && geo->fn_cj_same_exact) {
@@ -753,14 +776,16 @@ int launch_scan(msv_model* model, msv_db* db, size_t first, size_t count, uint64
             feedback = true;
             const unsigned int failures = model->h_speculation_totals[0], offered = model->h_speculation_totals[1];
             if (offered - model->seen_offered >= 4096u) { // unsigned differences: the totals may wrap
-                model->hits_are_common = 50ull * (failures - model->seen_failures) > (offered - model->seen_offered);
+                model->hit_share = static_cast<float>(failures - model->seen_failures) / static_cast<float>(offered - model->seen_offered);
                 model->seen_failures = failures;
                 model->seen_offered = offered;
             }
         }
-        const bool long_sequences = residues / count > 1024;
-        if (forced_mode == "none") kernel = geo->fn_cj_same_exact, feedback = false;
-        else if (forced_mode == "blocks" || (forced_mode != "whole" && (long_sequences || model->hits_are_common))) kernel = geo->fn_cj_same_blocks;
+        Rows rows = rows_for(geo->K, model->hit_share, residues / count > 1024);
+        if (forced_mode == "none") rows = kExact;
+        else if (forced_mode == "blocks") rows = kBlocks;
+        else if (forced_mode == "whole") rows = kWhole;
+        kernel = rows == kExact ? geo->fn_cj_same_exact : rows == kBlocks ? geo->fn_cj_same_blocks : geo->fn_cj_same;
     }
     if (feedback) p.speculation_failures = model->d_speculation_totals;
     kernel<<<static_cast<int>(ctas), threads, plan.shared_bytes, stream>>>(p);
@@ -1329,14 +1354,18 @@ int msv_cuda_model_wave_geometry(const msv_model* model, int* columns_per_lane, 
     return MSV_OK;
 }
 
-int msv_cuda_model_speculation(const msv_model* model, unsigned int* failed, unsigned int* offered, int* blocks_next) {
+int msv_cuda_model_speculation(const msv_model* model, unsigned int* failed, unsigned int* scanned, int* rows_next) {
     if (!model) return fail(MSV_ERR_INVALID_ARGUMENT, "model is NULL");
     const unsigned int f = model->h_speculation_totals ? model->h_speculation_totals[0] : 0u;
     const unsigned int o = model->h_speculation_totals ? model->h_speculation_totals[1] : 0u;
     if (failed) *failed = f;
-    if (offered) *offered = o;
-    if (blocks_next) // the decision launch_scan would take now (it also folds the totals in once 4096 new sequences are behind them)
-        *blocks_next = (o - model->seen_offered >= 4096u) ? 50ull * (f - model->seen_failures) > (o - model->seen_offered) : model->hits_are_common;
+    if (scanned) *scanned = o;
+    if (rows_next) { // the decision launch_scan would take now (it also folds the totals in once 4096 new sequences are behind them)
+        const float share = (o - model->seen_offered >= 4096u) ? static_cast<float>(f - model->seen_failures) / static_cast<float>(o - model->seen_offered)
+                                                                : model->hit_share;
+        const Geometry* geo = model->bulk.geo;
+        *rows_next = (geo && geo->fn_cj_same_exact) ? static_cast<int>(rows_for(geo->K, share, false)) : MSV_ROWS_EXACT;
+    }
     return MSV_OK;
 }
 

@@ -463,7 +463,10 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
 
     // never index the table with an unvalidated residue code: the validation kernel precedes this launch on the stream
     if (p.first_bad != nullptr && *p.first_bad != ~0ull) return;
-    if constexpr (SPEC) // [1] counts the sequences offered to speculation, [0] the failures among them (below)
+    // [1] counts the sequences scanned, [0] those whose speculation failed -- or, with exact rows, would have failed: once J
+    // exceeds N it stays >= N to the end of the sequence (both grow by the same + loop, and rounding is monotone), which is
+    // exactly what the speculating rows vote on.  The host picks the row variant of the next launch from these (launch_scan).
+    if constexpr (CJ_SAME)
         if (blockIdx.x == 0 && threadIdx.x == 0 && p.speculation_failures) atomicAdd(p.speculation_failures + 1, p.n);
 
     // ---- stage the shared-memory part with the TMA unit ----
@@ -769,6 +772,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
             }
         }
         }
+        if constexpr (CJ_SAME && !SPEC) // exact rows: the same statistic the speculating rows produce (see the top of the kernel)
+            if (lane == 0 && p.speculation_failures && J >= N) atomicAdd(p.speculation_failures, 1u);
         if (lane == 0) store_score(p, idx, (CJ_SAME ? J : C) + move); // MSV_HMM.cpp:112
     }
 

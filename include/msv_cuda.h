@@ -98,14 +98,17 @@ int msv_cuda_model_geometry(const msv_model* model, int* lanes_per_sequence, int
  * (0 = the model has no such plan either), warps in the chain, CTAs in the cluster.  Any pointer may be NULL. */
 int msv_cuda_model_wave_geometry(const msv_model* model, int* columns_per_lane, int* warps, int* ctas, int* diagonal_ctas);
 
-/* Speculative rows of the warp-per-sequence kernel (B = N + move while no hit has lifted J above N; verified, and repeated
- * exactly where the check fails -- same bits always).  Two variants exist: speculate on a whole sequence and rescan it on a
- * failed check (fastest when hits are rare), or speculate in checkpointed blocks of 64 rows (a hit costs one block).  The
- * library picks per launch: blocks when the sequences are long (mean above 1024 residues) or when more than 2 % of the
- * sequences of the previous scans with this model failed the check.  This reads the running totals behind that choice
- * (sequences that failed / that were offered to a speculating kernel, as of the last finished scan) and whether the next
- * scan of ordinary-length sequences would use blocks.  Any pointer may be NULL. */
-int msv_cuda_model_speculation(const msv_model* model, unsigned int* failed, unsigned int* offered, int* blocks_next);
+/* Row variants of the warp-per-sequence kernel -- the same bits always.  Exact rows compute B = max(N, J) + move from the
+ * row's E.  Speculative rows take B = N + move, which holds while no hit has lifted J above N, verify it, and repeat
+ * exactly what failed: on whole sequences (a failed sequence is scanned again: fastest when hits are rare) or in checkpointed
+ * blocks of 64 rows (a hit costs one block).  The library picks per launch from the model length, the mean sequence length
+ * and the share of sequences that failed (or, with exact rows, would have failed) the check in the previous scans with this
+ * model.  This reads the running totals behind that choice (as of the last finished scan) and the variant the next scan of
+ * ordinary-length sequences would use.  Any pointer may be NULL. */
+#define MSV_ROWS_EXACT 0
+#define MSV_ROWS_SPECULATE_WHOLE 1
+#define MSV_ROWS_SPECULATE_BLOCKS 2
+int msv_cuda_model_speculation(const msv_model* model, unsigned int* failed, unsigned int* scanned, int* rows_next);
 
 /* which launch plan a scan of the whole of `db` with `model` would use (introspection for tests and tuning): lanes per
  * sequence of the chosen kernel family (8, 32 or 128) and sequences in flight per CTA.  Does not launch anything. */

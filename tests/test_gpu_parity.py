@@ -737,20 +737,21 @@ def test_speculation_falls_back_exactly_on_hits(oracle, name, monkeypatch):
     # a database of long sequences only (mean length above the launch-level threshold) takes the block-wise kernel
     long_codes, long_offsets = pack(seqs[-12:])
     assert ubits(model.score_batch(long_codes, long_offsets)).tolist() == ubits(want[-12:]).tolist()
-    # feedback: after enough sequences of this hit-rich database the library switches to blocks by itself ...
+    # feedback: after enough sequences of this hit-rich database the library switches to exact rows by itself (they also count
+    # the sequences that would have failed the speculation) ...
     if model.plan(db)["lanes_per_sequence"] == 32 and model.geometry["columns_per_lane"] <= 44:
         for _ in range(3):
             assert ubits(db.score(model)).tolist() == ubits(want).tolist()
         state = model.speculation
-        assert state["offered"] >= 4096 and state["failed"] > state["offered"] // 4 and state["blocks_next"], state
-        # ... and back to whole sequences on a database without hits
+        assert state["scanned"] >= 4096 and state["failed"] > state["scanned"] // 4 and state["rows_next"] == "exact", state
+        # ... and back to speculation on whole sequences on a database without hits
         noise = [rng.integers(0, 20, size=int(rng.integers(50, 400)), dtype=np.uint8) for _ in range(5000)]
         noise_codes, noise_offsets = pack(noise)
         noise_want = oracle.score_batch(table, tr3, noise_codes, noise_offsets, threads=CORES)
         noise_db = msv.Database(noise_codes, noise_offsets)
         for _ in range(3):
             assert ubits(noise_db.score(model)).tolist() == ubits(noise_want).tolist()
-        assert not model.speculation["blocks_next"], model.speculation
+        assert model.speculation["rows_next"] == "whole", model.speculation
 
 
 @pytest.mark.parametrize("name,geometry", [("100.hmm", "8,16"), ("200.hmm", "8,28"), ("100.hmm", "4,28"), ("200.hmm", "4,52"),
