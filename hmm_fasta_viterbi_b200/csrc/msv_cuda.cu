@@ -101,7 +101,7 @@ template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_blocks
     else return nullptr;
 }
 template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_exact_kernel() {
-    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD>;
+    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD, 0, true>;
     else return nullptr;
 }
 template <int K, int KT> constexpr Geometry warp_entry() {

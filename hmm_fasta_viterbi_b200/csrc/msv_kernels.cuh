@@ -439,7 +439,10 @@ constexpr uint32_t kSpeculationBlockRows = MSV_SPEC_BLOCK_ROWS; // rows between 
 // schedules its plain loop 2-3 % better: 10.08 vs 9.85 TCUPS at K = 44, profiles/r02/variant_sweep_v3.txt) and loses a whole
 // extra pass per hit; mode 2 loses one block per hit.  The host picks per launch from the share of failed speculations it
 // observed in the previous scan of the same database (Scan_params::speculation_failures) and from the sequence lengths.
-template <int K, int KT, int THREADS, bool CJ_SAME, bool TMEM_AHEAD = false, int SPECULATE = 0>
+// REPORT: exact rows that also count the sequences which would have failed the speculation (only instantiated for the K that
+// have speculating variants to choose from: two more instructions per sequence cost up to 6 % at some K -- 2207.hmm 9.91 ->
+// 9.31 TCUPS -- through nothing but a different register allocation).
+template <int K, int KT, int THREADS, bool CJ_SAME, bool TMEM_AHEAD = false, int SPECULATE = 0, bool REPORT = false>
 __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_params p) {
     constexpr bool SPEC = SPECULATE != 0 && CJ_SAME;
     constexpr bool CHECKPOINTS = SPECULATE == 2 && CJ_SAME;
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
     // [1] counts the sequences scanned, [0] those whose speculation failed -- or, with exact rows, would have failed: once J
     // exceeds N it stays >= N to the end of the sequence (both grow by the same + loop, and rounding is monotone), which is
     // exactly what the speculating rows vote on.  The host picks the row variant of the next launch from these (launch_scan).
-    if constexpr (CJ_SAME)
+    if constexpr (CJ_SAME && (SPECULATE != 0 || REPORT))
         if (blockIdx.x == 0 && threadIdx.x == 0 && p.speculation_failures) atomicAdd(p.speculation_failures + 1, p.n);
 
     // ---- stage the shared-memory part with the TMA unit ----
@@ -772,7 +775,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
             }
         }
         }
-        if constexpr (CJ_SAME && !SPEC) // exact rows: the same statistic the speculating rows produce (see the top of the kernel)
+        if constexpr (CJ_SAME && !SPEC && REPORT) // exact rows: the same statistic the speculating rows produce (see the top of the kernel)
             if (lane == 0 && p.speculation_failures && J >= N) atomicAdd(p.speculation_failures, 1u);
         if (lane == 0) store_score(p, idx, (CJ_SAME ? J : C) + move); // MSV_HMM.cpp:112
     }
