@@ -679,6 +679,9 @@ def test_fused_gather_two_gpus(tmp_path):
     checked = [v for k, v in line["parity"].items() if k.startswith("gathered_job_buffer_vs_")]
     assert checked and checked[0]["mismatches"] == 0 and checked[0]["checked"] >= 1000
     # ... and the single-process driver behind the C ABI (msv_cuda_multi_score_batch) gives the same bits in every gather mode
+    # both forms of the gather (per-sequence stores from the scan kernel / a push kernel behind it) leave the whole job on every rank
+    for form in ("stores", "push"):
+        assert line["gather_forms"][form]["every_rank_holds_the_whole_job"] is True, line["gather_forms"]
     single = line["single_process_multi_gpu"]
     assert single["same_bits_as_multi_process_job_buffer"] is True, single
     for mode in ("peer", "nccl"):
