@@ -55,7 +55,7 @@ struct Geometry {
     int variant = 0;        // 0: tensor-memory columns are each lane's lowest; 1: TMEM_AHEAD (they are the highest, loaded a row ahead)
     Scan_kernel fn_cj_same_exact = nullptr; // warp family: when fn_cj_same speculates B = N + move (and verifies), the kernel that never does
     Scan_kernel fn_cj_same_blocks = nullptr; // warp family: speculation in checkpointed blocks (fn_cj_same speculates on whole sequences)
-    Scan_kernel fn_group_spec = nullptr;    // lane-group family (G = 8): speculative scan; failures go to a second, exact launch
+    Scan_kernel fn_group_spec = nullptr;    // lane-group family (G = 4, 8): speculative scan; a failed sequence is repeated exactly inside the kernel
     // (four lanes per sequence: two interleaved copies of the table, see msv_scan_kernel)
     // lane-group family with K % 4 == 2: the two highest columns of a lane are a pair behind the quads, 128 bytes per residue
     size_t shared_bytes() const {

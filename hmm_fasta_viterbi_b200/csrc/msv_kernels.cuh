@@ -8,7 +8,7 @@
 // Three kernel families share one design (B200-first, not a translation):
 //   msv_scan_warp_kernel        one warp per sequence; emissions from shared memory AND tensor memory   -- the hot kernel
 //   msv_scan_kernel             G = 8/16/32 lanes per sequence, 32/G sequences per warp                  -- short models
-//   msv_scan_group_spec_kernel  the same with speculative rows + a device-side redo list                 -- shortest models
+//   msv_scan_group_spec_kernel  the same with speculative rows, failed sequences repeated exactly in place -- short models (default)
 //   msv_scan_quad_kernel        four warps per sequence; table distributed over shared + tensor memory   -- few/long sequences,
 //                                                                                                          models > 2815 columns
 // Common to all:
