@@ -20,6 +20,7 @@
 
 #include "msv_internal.hpp"
 #include "msv_kernels.cuh"
+#include "msv_registry.hpp"
 #include "msv_wave_kernels.cuh"
 
 static thread_local std::string g_last_error;
@@ -40,136 +41,30 @@ void count_launch() { ++g_launches; }
 
 namespace {
 
-// ---- kernel registry ------------------------------------------------------------------------------------------------
-// Two kernel families (msv_kernels.cuh):
-//   generic : G = 8/16/32 lanes per sequence, whole table in shared memory           (KT = -1 below)
-//   warp    : G = 32, table split between shared memory and KT tensor-memory columns per lane (KT = 0, 8, 16, 24)
-constexpr int threads_for(int K) { return K <= 20 ? 1024 : K <= 40 ? 768 : K <= 56 ? 640 : 512; }
-constexpr int warp_threads_for(int K, int KT) { return K + (KT > 0 ? 8 : 0) <= 24 ? 1024 : K <= 30 ? 768 : K <= 36 ? 640 : 512; }
+// ---- kernel registry: msv_registry.hpp; the table is compiled in four parts and joined here ---------------------------
+using msv_registry::Geometry;
+using msv_registry::Scan_kernel;
+using msv_registry::Rows;
+using msv_registry::kExact;
+using msv_registry::kWhole;
+using msv_registry::kBlocks;
+using msv_registry::quiet_rows;
 
-using Scan_kernel = void (*)(const msv::Scan_params);
-struct Geometry {
-    int G, K, KT, threads;
-    Scan_kernel fn;         // general transitions
-    Scan_kernel fn_cj_same; // tr_E_C == tr_E_J bitwise (C is J); same as fn for the generic family
-    int variant = 0;        // 0: tensor-memory columns are each lane's lowest; 1: TMEM_AHEAD (they are the highest, loaded a row ahead)
-    Scan_kernel fn_cj_same_exact = nullptr; // warp family: when fn_cj_same speculates B = N + move (and verifies), the kernel that never does
-    Scan_kernel fn_cj_same_blocks = nullptr; // warp family: speculation in checkpointed blocks (fn_cj_same speculates on whole sequences)
-    Scan_kernel fn_group_spec = nullptr;    // lane-group family (G = 4, 8): speculative scan; a failed sequence is repeated exactly inside the kernel
-    // (four lanes per sequence: two interleaved copies of the table, see msv_scan_kernel)
-    // lane-group family with K % 4 == 2: the two highest columns of a lane are a pair behind the quads, 128 bytes per residue
-    size_t shared_bytes() const {
-        if (KT < 0) return static_cast<size_t>(MSV_ALPHABET) * (static_cast<size_t>(K / 4) * std::max(G, 8) * 16 + (K % 4 ? 128 : 0));
-        return static_cast<size_t>(MSV_ALPHABET) * (K - KT) * G * sizeof(float);
-    }
-};
-
-// speculative lane-group scan.  Round 1 (failed speculations went to a second launch): ahead of the exact one by 15 % at
-// K = 16 and behind it from K = 40 up.  With the exact redo inside the kernel (round 2) it is ahead everywhere the lane-group
-// plans are used: 300.hmm (8 x 38) 6.53 -> 8.13 TCUPS, 400.hmm (8 x 52) 7.00 -> 8.16 on 100 k sequences
-// (profiles/r02/group_spec_sweep_v1.txt); beyond K = 56 the warp-per-sequence kernel wins anyway (group_spec_sweep_v2.txt)
-template <int G, int K> constexpr Scan_kernel group_spec_kernel() {
-    if constexpr ((G == 8 && K <= 56) || G == 4) return msv::msv_scan_group_spec_kernel<G, K, threads_for(K)>;
-    else return nullptr;
+const std::vector<Geometry>& all_geometries() {
+    static const std::vector<Geometry> table = [] {
+        std::vector<Geometry> t;
+        for (auto part : {msv_registry::part0, msv_registry::part1, msv_registry::part2, msv_registry::part3}) {
+            size_t count = 0;
+            const Geometry* entries = part(&count);
+            t.insert(t.end(), entries, entries + count);
+        }
+        return t;
+    }();
+    return table;
 }
-template <int G, int K> constexpr Geometry generic_entry() {
-    return Geometry{G, K, -1, threads_for(K), msv::msv_scan_kernel<G, K, threads_for(K), false>,
-                    msv::msv_scan_kernel<G, K, threads_for(K), true>, 0, nullptr, nullptr, group_spec_kernel<G, K>()};
-}
-// Speculative rows (B = N + move, verified per sequence; msv_kernels.cuh) are instantiated where B200 sweeps showed them
-// ahead of the exact rows (profiles/r01/sweep_speculation*.txt: +13 % at K = 4, +2..6 % at K = 16..22 and 32..38, level at
-// K = 8..14 and 42, 44; behind by 1 % at K = 26..30 and by 5..8 % from K = 48 up, where the two row bodies no longer share
-// the instruction cache).
-// The row variant of the warp kernel that is fastest on a database WITHOUT hits, per columns-per-lane K: B200 sweep over the
-// fixture models, profiles/r02/speculation_sweep_v2.txt (100 k sequences; exact / whole-sequence / block-wise speculation, e.g.
-// K = 44: 9.76 / 10.05 / 9.77 TCUPS, K = 38: 9.16 / 9.32 / 9.57, K = 42: 9.41 / 9.29 / 9.08, K = 48: 9.87 / 9.63 / 8.91).
-// It is not monotone in K -- the compiler's schedule of three different loop nests at the register limit -- and beyond
-// K = 44 the two row bodies no longer share the instruction cache.  Unmeasured K keep round 1's rule.
-enum Rows { kExact = 0, kWhole = 1, kBlocks = 2 };
-constexpr Rows quiet_rows(int K) {
-    if (K > 44 || K == 26 || K == 28 || K == 42) return kExact;
-    if (K == 16 || K == 38) return kBlocks;
-    return kWhole;
-}
-constexpr bool speculation_pays(int K) { return quiet_rows(K) != kExact; }
-template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_kernel() {
-    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD, 1>;
-    else return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD>;
-}
-template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_blocks_kernel() {
-    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD, 2>;
-    else return nullptr;
-}
-template <int K, int KT, int T, bool AHEAD> constexpr Scan_kernel cj_same_exact_kernel() {
-    if constexpr (speculation_pays(K)) return msv::msv_scan_warp_kernel<K, KT, T, true, AHEAD, 0, true>;
-    else return nullptr;
-}
-template <int K, int KT> constexpr Geometry warp_entry() {
-    return Geometry{32, K, KT, warp_threads_for(K, KT), msv::msv_scan_warp_kernel<K, KT, warp_threads_for(K, KT), false>,
-                    cj_same_kernel<K, KT, warp_threads_for(K, KT), false>(), 0, cj_same_exact_kernel<K, KT, warp_threads_for(K, KT), false>(),
-                    cj_same_blocks_kernel<K, KT, warp_threads_for(K, KT), false>()};
-}
-
-constexpr int quad_threads_for(int K) { return K <= 12 ? 1024 : K <= 28 ? 768 : 512; }
-template <int K, int KT> constexpr Geometry quad_entry() { // four warps (128 lanes) per sequence
-    return Geometry{128, K, KT, quad_threads_for(K), msv::msv_scan_quad_kernel<K, KT, quad_threads_for(K), false>,
-                    msv::msv_scan_quad_kernel<K, KT, quad_threads_for(K), true>};
-}
-template <int K, int KT, int T> constexpr Geometry warp_entry_threads() {
-    return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false>, cj_same_kernel<K, KT, T, false>(), 0,
-                    cj_same_exact_kernel<K, KT, T, false>(), cj_same_blocks_kernel<K, KT, T, false>()};
-}
-
-template <int K, int KT, int T> constexpr Geometry warp_entry_ahead() {
-    return Geometry{32, K, KT, T, msv::msv_scan_warp_kernel<K, KT, T, false, true>, cj_same_kernel<K, KT, T, true>(), 1,
-                    cj_same_exact_kernel<K, KT, T, true>(), cj_same_blocks_kernel<K, KT, T, true>()};
-}
-
-#define MSV_FOR_EACH_K(X, A)                                                                                           \
-    X(A, 4) X(A, 8) X(A, 12) X(A, 16) X(A, 20) X(A, 24) X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52)  \
-    X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) X(A, 76) X(A, 80) X(A, 84) X(A, 88)
-#define MSV_FOR_EACH_K_FROM_24(X, A)                                                                                   \
-    X(A, 24) X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) \
-    X(A, 76) X(A, 80) X(A, 84) X(A, 88)
-#define MSV_GENERIC(G, K) generic_entry<G, K>(),
-#define MSV_WARP(KT, K) warp_entry<K, KT>(),
-#define MSV_WARP_AHEAD(KT, K) warp_entry_ahead<K, KT, warp_threads_for(K, KT)>(),
-#define MSV_FOR_EACH_K_FROM_28(X, A)                                                                                   \
-    X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56) X(A, 60) X(A, 64) X(A, 68) X(A, 72) X(A, 76)  \
-    X(A, 80) X(A, 84) X(A, 88)
-#ifdef MSV_QUICK_BUILD // development aid: only what a 1400-column model needs, so that a kernel experiment compiles in seconds
-const Geometry g_geometries[] = {generic_entry<32, 44>(), warp_entry_ahead<44, 24, 512>(), warp_entry<44, 16>(), quad_entry<12, 8>(),
-                                 generic_entry<4, 28>(), generic_entry<8, 16>()
-#ifdef MSV_QUICK_EXTRA
-                                 , MSV_QUICK_EXTRA
-#endif
-};
-#else
-#define MSV_FOR_EACH_K_TO_56(X, A)                                                                                     \
-    X(A, 4) X(A, 8) X(A, 12) X(A, 16) X(A, 20) X(A, 24) X(A, 28) X(A, 32) X(A, 36) X(A, 40) X(A, 44) X(A, 48) X(A, 52) X(A, 56)
-// lane groups with K % 4 == 2 (less padding for the short models; G = 4 and 8 only)
-#define MSV_FOR_EACH_K_PAIR(X, A)                                                                                      \
-    X(A, 6) X(A, 10) X(A, 14) X(A, 18) X(A, 22) X(A, 26) X(A, 30) X(A, 34) X(A, 38) X(A, 42) X(A, 46) X(A, 50) X(A, 54)
-const Geometry g_geometries[] = {MSV_FOR_EACH_K_TO_56(MSV_GENERIC, 4) MSV_FOR_EACH_K(MSV_GENERIC, 8) MSV_FOR_EACH_K(MSV_GENERIC, 16) MSV_FOR_EACH_K(MSV_GENERIC, 32)
-                                     MSV_FOR_EACH_K_PAIR(MSV_GENERIC, 4) MSV_FOR_EACH_K_PAIR(MSV_GENERIC, 8)
-                                     MSV_WARP(0, 4) MSV_WARP(0, 8) MSV_WARP(8, 8) MSV_WARP(8, 12) MSV_WARP(8, 16) MSV_WARP(8, 20)
-                                         MSV_WARP(16, 16) MSV_WARP(16, 20) MSV_WARP(24, 24) MSV_FOR_EACH_K_FROM_24(MSV_WARP, 16)
-                                             MSV_FOR_EACH_K_FROM_28(MSV_WARP, 24) MSV_WARP(0, 44) MSV_WARP(8, 44)
-                                                 warp_entry_threads<44, 16, 640>(), warp_entry_threads<44, 16, 448>(),
-                                 warp_entry_threads<44, 16, 384>(), MSV_FOR_EACH_K_FROM_24(MSV_WARP_AHEAD, 16)
-                                     MSV_FOR_EACH_K_FROM_28(MSV_WARP_AHEAD, 24) MSV_WARP_AHEAD(16, 16) MSV_WARP_AHEAD(16, 20)
-                                         MSV_WARP_AHEAD(8, 8) MSV_WARP_AHEAD(8, 12)
-                                 // columns per lane in steps of two (less padding): tensor-memory part 18 = 16 + 2 columns
-                                 MSV_WARP_AHEAD(6, 6) MSV_WARP_AHEAD(10, 10) MSV_WARP_AHEAD(14, 14) MSV_WARP_AHEAD(18, 18) MSV_WARP_AHEAD(18, 22)
-                                 MSV_WARP_AHEAD(18, 26) MSV_WARP_AHEAD(18, 30) MSV_WARP_AHEAD(18, 34) MSV_WARP_AHEAD(18, 38) MSV_WARP_AHEAD(18, 42)
-                                 MSV_WARP_AHEAD(18, 46) MSV_WARP_AHEAD(18, 50) MSV_WARP_AHEAD(18, 54) MSV_WARP_AHEAD(18, 58)
-                                 quad_entry<4, 0>(), quad_entry<8, 8>(), quad_entry<12, 8>(), quad_entry<16, 16>(), quad_entry<20, 16>(),
-                                 quad_entry<24, 16>(), quad_entry<28, 16>(), quad_entry<32, 16>(), quad_entry<36, 16>(),
-                                 quad_entry<40, 24>(), quad_entry<44, 24>()};
-#endif
 
 const Geometry* find_geometry(int G, int K, int KT, int threads = 0, int variant = 0) {
-    for (const auto& g : g_geometries)
+    for (const auto& g : all_geometries())
         if (g.G == G && g.K == K && g.KT == KT && (threads == 0 || g.threads == threads) && g.variant == variant) return &g;
     return nullptr;
 }
@@ -238,7 +133,7 @@ const Geometry* choose_narrow_geometry(size_t columns) {
 // Four warps per sequence: the plan for few/long sequences and for models beyond one warp's registers.
 const Geometry* choose_quad_geometry(size_t columns) {
     const int K = std::max(4, round_up4((columns + 127) / 128));
-    for (const auto& g : g_geometries)
+    for (const auto& g : all_geometries())
         if (g.G == 128 && g.K == K) return &g;
     return nullptr;
 }

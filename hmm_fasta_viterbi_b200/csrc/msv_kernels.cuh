@@ -987,6 +987,7 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_quad_kernel(const Scan_pa
     }
 }
 
+#ifndef MSV_KERNELS_TEMPLATES_ONLY // (the registry parts include this file for the kernel templates only)
 // ---- gather of a sharded run, "push" form: after the scan, this GPU's slice of the job's score array (its own copy) is
 // written into every peer's copy with coalesced stores over NVLink (128 bytes per warp instruction and peer).  The other
 // form stores each score into all copies from the scan kernel itself (store_score); see launch_scan for which is used when.
@@ -1088,5 +1089,7 @@ __global__ void msv_filter_statistics_kernel(const float* __restrict__ scores, c
     if (bits_out) bits_out[q] = static_cast<float>(bits);
     if (p_out) p_out[q] = static_cast<float>(p);
 }
+
+#endif // MSV_KERNELS_TEMPLATES_ONLY
 
 } // namespace msv
