@@ -616,8 +616,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         // 4 rows (one residue word) per loop iteration, 8 or 16 where B200 sweeps showed a gain (+1..4 %, +10 % at K = 4;
         // profiles/r01/sweep_models_v6_row_unroll.jsonl, sweep_force_unroll2.txt).  It is not monotone in K -- the
         // instruction scheduler's luck -- and the longest bodies stop fitting the instruction cache (-10 % at K = 76).
-        constexpr bool EIGHT_ROWS = K == 20 || K == 30 || K == 32 || K == 36 || K == 42 || K == 44 || K == 52 || K == 54 || K == 58 ||
-                                    K == 60 || K == 68;
+        constexpr bool EIGHT_ROWS = K == 20 || K == 30 || K == 32 || K == 36 || K == 42 || K == 44 || K == 52 || K == 58 ||
+                                    K == 60; // (K = 68 was in this list in round 1; re-measured: 9.25 TCUPS with 8 rows, 10.24 with 4 -- profiles/r02/unroll_sweep_v1/v2.txt; K = 54 likewise, by 0.6 %)
 #ifdef MSV_FORCE_UNROLL // development aid (with MSV_QUICK_BUILD)
         constexpr int WORD_UNROLL = MSV_FORCE_UNROLL;
 #else
@@ -672,8 +672,8 @@ __global__ void __launch_bounds__(THREADS, 1) msv_scan_warp_kernel(const Scan_pa
         // 4 rows (one residue word) per loop iteration, 8 or 16 where B200 sweeps showed a gain (+1..4 %, +10 % at K = 4;
         // profiles/r01/sweep_models_v6_row_unroll.jsonl, sweep_force_unroll2.txt).  It is not monotone in K -- the
         // instruction scheduler's luck -- and the longest bodies stop fitting the instruction cache (-10 % at K = 76).
-        constexpr bool EIGHT_ROWS = K == 20 || K == 30 || K == 32 || K == 36 || K == 42 || K == 44 || K == 52 || K == 54 || K == 58 ||
-                                    K == 60 || K == 68;
+        constexpr bool EIGHT_ROWS = K == 20 || K == 30 || K == 32 || K == 36 || K == 42 || K == 44 || K == 52 || K == 58 ||
+                                    K == 60; // (K = 68 was in this list in round 1; re-measured: 9.25 TCUPS with 8 rows, 10.24 with 4 -- profiles/r02/unroll_sweep_v1/v2.txt; K = 54 likewise, by 0.6 %)
 #ifdef MSV_FORCE_UNROLL // development aid (with MSV_QUICK_BUILD)
         constexpr int WORD_UNROLL = MSV_FORCE_UNROLL;
 #else
