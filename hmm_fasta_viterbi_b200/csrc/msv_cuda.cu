@@ -103,12 +103,13 @@ const Geometry* choose_geometry(size_t columns) {
         case 4: return {0, 0};
         case 8: case 12: return {8, 1};
         case 16: return {16, 1};
-        case 20: return {16, 0};
+        case 20: return {16, 1}; // (round 2, profiles/r02/kt_sweep_v1.txt: 8.65 vs 8.40 TCUPS for the row-ahead variant)
         case 24: case 28: return {16, 1};
         case 32: case 36: return {24, 1};
         case 40: return {16, 1};
         case 44: return {24, 1};
-        case 48: case 52: case 56: return {16, 1};
+        case 52: return {16, 0}; // (round 2, kt_sweep_v1.txt: 9.52 vs 9.35 TCUPS)
+        case 48: case 56: return {16, 1};
         default: return {24, 1}; // 60 .. 88
         }
     };
