@@ -758,11 +758,12 @@ int score_batch_pipelined(msv_model* model, msv_db* db, const uint8_t* residues,
     std::vector<uint32_t> stage_counts;
     std::vector<uint64_t> stage_rows;
     const auto enqueue = [&]() -> int {
-        MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy));
         MSV_CUDA_TRY(cudaMemsetAsync(db->d_residues + total, 0, msv::kResiduePadBytes + 16, copy));
         for (int s = 0; s < stages; ++s) {
             const size_t first = bounds[s], last = bounds[s + 1];
             const uint64_t begin = offsets[first], end = offsets[last];
+            // the stage's own offsets travel with it (8 MB for a million sequences would otherwise delay the first scan by 0.15 ms)
+            MSV_CUDA_TRY(cudaMemcpyAsync(db->d_offsets + first, offsets + first, (last - first + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, copy));
             if (end > begin)
                 MSV_CUDA_TRY(cudaMemcpyAsync(db->d_residues + begin, residues + begin, end - begin, cudaMemcpyHostToDevice, copy));
             cudaStream_t const lane = lanes[s & 1];
